@@ -1,0 +1,43 @@
+"""Programs used across the parity tests.  They follow the reference's own end-to-end tests
+(/root/reference/src/tests/mod.rs:12-309, tests/comparisons.rs) and example programs (src/examples/*.rs)."""
+from distaff_b200 import hostvm
+
+
+def merkle_example(depth, po):
+    """examples/merkle.rs:60-108 (authentication path drawn from field::prng_vector with the example's two seeds)"""
+    s1 = bytes([1, 2, 3] + [0] * 29)
+    s2 = bytes([4, 5, 6] + [0] * 29)
+    p0, p1 = po.prng_vector(s1, depth), po.prng_vector(s2, depth)
+    leaf_index = p0[0] % (2 ** (depth - 1))
+    a, b = [p0[0]], [p1[0]]
+    index = leaf_index + 2 ** (depth - 1)
+    for i in range(1, depth):
+        a += [0, p0[i]]
+        b += [index & 1, p1[i]]
+        index >>= 1
+    for i in range(1, depth):
+        a.append(p0[i])
+        b.append(p1[i])
+    return hostvm.execute(hostvm.merkle_program(depth, leaf_index), secret_a=a, secret_b=b, num_outputs=4)
+
+
+def small_programs():
+    """name -> ExecutionTrace ; all have 2^6..2^9 steps so the CPU oracle proves each in well under a second"""
+    P = {}
+    P["fib13"] = hostvm.fibonacci(13)                                              # BASELINE configs[0]
+    P["fib_span"] = hostvm.execute("begin swap dup.2 drop add swap dup.2 drop add swap dup.2 drop add end",
+                                   public_inputs=[1, 0])                           # tests/mod.rs:12-29
+    P["stack_ops"] = hostvm.execute("begin swap swap.2 swap.4 roll.4 roll.8 pad.2 drop.2 dup dup.2 dup.4 drop.8 end",
+                                    public_inputs=[1, 2, 3, 4, 5, 6, 7, 8], num_outputs=8)
+    P["logic"] = hostvm.execute("begin not and or end", public_inputs=[1, 1, 0, 1], num_outputs=2)   # tests/mod.rs logic_operations
+    P["arith"] = hostvm.execute("begin add mul inv neg push.3 sub push.9 div end", public_inputs=[2, 3, 4], num_outputs=1)
+    P["eq"] = hostvm.execute("begin eq swap.2 ne and end", public_inputs=[5, 5, 9, 6, 7], num_outputs=1)
+    P["cmp"] = hostvm.execute("begin push.5 push.11 gt.8 push.7 push.3 lt.8 and end", num_outputs=1)      # tests/comparisons.rs
+    P["rc"] = hostvm.execute("begin push.200 rc.8 push.300 rc.8 end", num_outputs=2)
+    P["choose"] = hostvm.execute("begin choose swap.2 choose.2 end", public_inputs=[3, 4, 1, 5, 6, 7, 0, 8], num_outputs=3)
+    P["hash"] = hostvm.execute("begin pad.2 hash.2 end", public_inputs=[5, 6], num_outputs=2)             # tests/mod.rs hash_operations
+    P["if_else"] = hostvm.execute("begin push.3 push.5 read if.true add else mul end end", secret_a=[1], num_outputs=1)
+    P["if_else0"] = hostvm.execute("begin push.3 push.5 read if.true add else mul end end", secret_a=[0], num_outputs=1)
+    P["nested"] = hostvm.execute("begin push.2 block push.3 block push.4 add end mul end add end", public_inputs=[1], num_outputs=1)
+    P["collatz3"] = hostvm.collatz(3)                                                                  # loop + switch + isodd
+    return P
