@@ -1,0 +1,299 @@
+// extern "C" surface declared in include/distaff_gpu.h.  Every entry point catches dg::Error and returns a code.
+#include "../../include/distaff_gpu.h"
+#include "common.cuh"
+#include "prover.h"
+
+namespace dg {
+void hash_trace_rows(Context &c, const fe *ext, void *leaves, int w, int log_n, int log_blowup);
+void merkle_build(Context &c, const void *leaves, void *nodes, unsigned long long L);
+unsigned long long pow_search(Context &c, const uint8_t seed[32], unsigned grinding);
+void pow_hash(const uint8_t seed[32], unsigned long long nonce, uint8_t out[32]);
+void hash_rows_plain(Context &c, const fe *cols, void *digests, int w, unsigned long long rows);
+}  // namespace dg
+
+using namespace dg;
+
+static thread_local std::string t_last_error;
+
+template <typename F>
+static int guarded(F &&f) {
+    try {
+        f();
+        return DG_OK;
+    } catch (const dg::Error &e) {
+        t_last_error = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        t_last_error = e.what();
+        return DG_ERR_INVALID;
+    }
+}
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    float *out;
+    EventTimer(cudaStream_t stream, float *ms) : s(stream), out(ms) {
+        if (!out) return;
+        DG_CUDA(cudaEventCreate(&a));
+        DG_CUDA(cudaEventCreate(&b));
+        DG_CUDA(cudaEventRecord(a, s));
+    }
+    void stop() {
+        if (!out) return;
+        DG_CUDA(cudaEventRecord(b, s));
+        DG_CUDA(cudaEventSynchronize(b));
+        DG_CUDA(cudaEventElapsedTime(out, a, b));
+    }
+    ~EventTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
+// ---- helper kernels ------------------------------------------------------------------------------------------------------
+__global__ void coset_to_logical_kernel(const fe *__restrict__ in, fe *__restrict__ out, int log_n, int log_blowup) {
+    const unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long N = 1ULL << (log_n + log_blowup);
+    if (p >= N) return;
+    const unsigned long long k = p & ((1ULL << log_n) - 1ULL), c = p >> log_n;
+    out[(unsigned long long)blockIdx.y * N + (k << log_blowup) + c] = in[(unsigned long long)blockIdx.y * N + p];
+}
+
+__global__ void field_op_kernel(int op, int impl, const fe *a, const fe *b, fe *out, unsigned long long n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fe x = a[i], y = b ? b[i] : fe_make(0, 0), r;
+    if (impl == 0) {
+        switch (op) {
+            case 0: r = fe_add(x, y); break;
+            case 1: r = fe_sub(x, y); break;
+            case 2: r = fe_mul(x, y); break;
+            case 3: r = fe_inv(x); break;
+            default: r = fe_is_zero(x) ? fe_make(0, 0) : fe_pow_u128(x, y.lo, y.hi); break;
+        }
+    } else {
+        switch (op) {
+            case 0: r = portable::fe_add(x, y); break;
+            case 1: r = portable::fe_sub(x, y); break;
+            case 2: r = portable::fe_mul(x, y); break;
+            case 3: r = portable::fe_inv(x); break;
+            default: r = fe_is_zero(x) ? fe_make(0, 0) : portable::fe_pow_u128(x, y.lo, y.hi); break;
+        }
+    }
+    out[i] = r;
+}
+
+__global__ void fill_kernel(uint4 *p, size_t n, unsigned v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = make_uint4(v, v + 1, v + 2, v + 3);
+}
+
+extern "C" {
+
+int dg_init(int device) { return guarded([&] { ctx_init(device); }); }
+const char *dg_last_error(void) { return t_last_error.c_str(); }
+
+int dg_device_info(char *name, size_t cap, int *sm_count, size_t *total_mem) {
+    return guarded([&] {
+        Context &c = ctx();
+        cudaDeviceProp prop;
+        DG_CUDA(cudaGetDeviceProperties(&prop, c.device));
+        if (name && cap) { strncpy(name, prop.name, cap - 1); name[cap - 1] = 0; }
+        if (sm_count) *sm_count = prop.multiProcessorCount;
+        if (total_mem) *total_mem = prop.totalGlobalMem;
+    });
+}
+
+// ---- device memory -------------------------------------------------------------------------------------------------------
+int dg_dev_alloc(void **ptr, size_t bytes) { return guarded([&] { ctx(); DG_CUDA(cudaMalloc(ptr, bytes)); }); }
+int dg_dev_free(void *ptr) { return guarded([&] { ctx(); DG_CUDA(cudaFree(ptr)); }); }
+int dg_dev_upload(void *dst, const void *src, size_t bytes) {
+    return guarded([&] { Context &c = ctx(); DG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.stream)); DG_CUDA(cudaStreamSynchronize(c.stream)); });
+}
+int dg_dev_download(void *dst, const void *src, size_t bytes) {
+    return guarded([&] { Context &c = ctx(); DG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream)); DG_CUDA(cudaStreamSynchronize(c.stream)); });
+}
+int dg_dev_sync(void) { return guarded([&] { DG_CUDA(cudaStreamSynchronize(ctx().stream)); }); }
+int dg_dev_flush_l2(void) {
+    return guarded([&] {
+        Context &c = ctx();
+        static DevBuf scratch;
+        const size_t bytes = (size_t)256 << 20;
+        scratch.ensure(bytes);
+        fill_kernel<<<(unsigned)(bytes / 16 / 256), 256, 0, c.stream>>>(scratch.as<uint4>(), bytes / 16, 7u);
+        DG_CUDA(cudaGetLastError());
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+// ---- device-resident building blocks ----------------------------------------------------------------------------------------
+int dg_dev_ntt(void *d_values, uint32_t log_n, uint32_t batch, int inverse, float *ms) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        c.twiddle(log_n, inverse != 0);       // table setup outside the timed region
+        if (log_n > 20) c.twiddle(log_n - (log_n + 2) / 3, inverse != 0);
+        c.ntt_tmp.ensure(((size_t)16 << log_n) * std::min<size_t>(batch, std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)16 << log_n))));
+        EventTimer t(c.stream, ms);
+        ntt_batch(c, (const fe *)d_values, (fe *)d_values, log_n, batch, (size_t)1 << log_n, (size_t)1 << log_n, inverse != 0);
+        t.stop();
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int dg_dev_lde(const void *d_polys, void *d_ext, uint32_t log_n, uint32_t log_blowup, uint32_t batch, float *ms) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        c.twiddle(log_n + log_blowup, false);
+        c.twiddle(log_n, false);
+        if (log_n > 20) c.twiddle(log_n - (log_n + 2) / 3, false);
+        EventTimer t(c.stream, ms);
+        lde_batch(c, (const fe *)d_polys, (fe *)d_ext, log_n, log_blowup, 1, batch, (size_t)1 << log_n, (size_t)1 << (log_n + log_blowup));
+        t.stop();
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int dg_dev_merkle_build(const void *d_leaves, uint64_t n_leaves, void *d_nodes, float *ms) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        EventTimer t(c.stream, ms);
+        merkle_build(c, d_leaves, d_nodes, n_leaves);
+        t.stop();
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int dg_dev_hash_rows(const void *d_ext, uint32_t width, uint32_t log_n, uint32_t log_blowup, void *d_leaves, float *ms) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(width >= 1 && width < 128, "width must be in 1..127");
+        EventTimer t(c.stream, ms);
+        hash_trace_rows(c, (const fe *)d_ext, d_leaves, (int)width, (int)log_n, (int)log_blowup);
+        t.stop();
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+// ---- host-memory building blocks -----------------------------------------------------------------------------------------------
+int dg_ntt(uint8_t *values, uint32_t log_n, uint32_t batch, int inverse) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(log_n >= 1 && log_n <= 30 && batch >= 1, "invalid transform size");
+        const size_t bytes = ((size_t)16 << log_n) * batch;
+        DevBuf d(bytes);
+        DG_CUDA(cudaMemcpyAsync(d.p, values, bytes, cudaMemcpyHostToDevice, c.stream));
+        ntt_batch(c, d.as<fe>(), d.as<fe>(), log_n, batch, (size_t)1 << log_n, (size_t)1 << log_n, inverse != 0);
+        DG_CUDA(cudaMemcpyAsync(values, d.p, bytes, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int dg_lde(const uint8_t *values, uint8_t *extended, uint32_t log_n, uint32_t log_blowup, uint32_t batch) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(log_n >= 1 && log_blowup >= 1 && log_n + log_blowup <= 30 && batch >= 1 && batch <= 65535, "invalid extension size");
+        const size_t n = (size_t)1 << log_n, N = n << log_blowup;
+        DevBuf d_in(n * batch * 16), d_ext(N * batch * 16), d_out(N * batch * 16);
+        DG_CUDA(cudaMemcpyAsync(d_in.p, values, n * batch * 16, cudaMemcpyHostToDevice, c.stream));
+        ntt_batch(c, d_in.as<fe>(), d_in.as<fe>(), log_n, batch, n, n, true);                 // interpolate (trace_table.rs:158)
+        lde_batch(c, d_in.as<fe>(), d_ext.as<fe>(), log_n, log_blowup, 1, batch, n, N);       // evaluate over the LDE domain (:165)
+        coset_to_logical_kernel<<<dim3((unsigned)((N + 255) / 256), batch), 256, 0, c.stream>>>(d_ext.as<fe>(), d_out.as<fe>(), log_n, log_blowup);
+        DG_CUDA(cudaGetLastError());
+        DG_CUDA(cudaMemcpyAsync(extended, d_out.p, N * batch * 16, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int dg_merkle_build(const uint8_t *leaves, uint64_t n_leaves, uint8_t *nodes) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(n_leaves >= 2 && (n_leaves & (n_leaves - 1)) == 0, "number of leaves must be a power of 2 and >= 2");
+        DevBuf d_l(n_leaves * 32), d_n(n_leaves * 32);
+        DG_CUDA(cudaMemcpyAsync(d_l.p, leaves, n_leaves * 32, cudaMemcpyHostToDevice, c.stream));
+        merkle_build(c, d_l.p, d_n.p, n_leaves);
+        DG_CUDA(cudaMemcpyAsync(nodes, d_n.p, n_leaves * 32, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int dg_hash_rows(const uint8_t *columns, uint32_t width, uint64_t rows, uint8_t *digests) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(width >= 1 && width < 128 && rows >= 1, "invalid matrix shape");
+        DevBuf d_c((size_t)width * rows * 16), d_d(rows * 32);
+        DG_CUDA(cudaMemcpyAsync(d_c.p, columns, (size_t)width * rows * 16, cudaMemcpyHostToDevice, c.stream));
+        // reuse the trace-row kernel with a single "coset": physical position == logical row
+        hash_rows_plain(c, d_c.as<fe>(), d_d.p, (int)width, rows);
+        DG_CUDA(cudaMemcpyAsync(digests, d_d.p, rows * 32, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int dg_find_pow_nonce(const uint8_t seed[32], uint32_t grinding_factor, uint64_t *nonce, uint8_t new_seed[32]) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(grinding_factor <= 32, "grinding factor cannot be greater than 32");
+        unsigned long long n = pow_search(c, seed, grinding_factor);
+        *nonce = n;
+        if (new_seed) pow_hash(seed, n, new_seed);
+    });
+}
+int dg_field_op(int op, int impl, const uint8_t *a, const uint8_t *b, uint8_t *out, uint64_t n) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        DevBuf da(n * 16), db(n * 16), dout(n * 16);
+        DG_CUDA(cudaMemcpyAsync(da.p, a, n * 16, cudaMemcpyHostToDevice, c.stream));
+        if (b) DG_CUDA(cudaMemcpyAsync(db.p, b, n * 16, cudaMemcpyHostToDevice, c.stream));
+        field_op_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(op, impl, da.as<fe>(), b ? db.as<fe>() : nullptr, dout.as<fe>(), n);
+        DG_CUDA(cudaGetLastError());
+        DG_CUDA(cudaMemcpyAsync(out, dout.p, n * 16, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+
+// ---- prover ------------------------------------------------------------------------------------------------------------------------
+int dg_prove(const dg_trace_t *trace, const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs,
+             const dg_options_t *options, dg_proof_t **proof_out, dg_prove_stats_t *stats) {
+    return guarded([&] {
+        DG_REQUIRE(trace && options && proof_out, "null argument");
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        *proof_out = (dg_proof_t *)prove_host(c, *trace, inputs16, n_inputs, outputs16, n_outputs, *options, stats);
+    });
+}
+int dg_prove_device(const void *d_registers, uint32_t width, uint64_t length, uint32_t ctx_depth, uint32_t loop_depth,
+                    const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs,
+                    const dg_options_t *options, dg_proof_t **proof_out, dg_prove_stats_t *stats) {
+    return guarded([&] {
+        DG_REQUIRE(d_registers && options && proof_out, "null argument");
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        *proof_out = (dg_proof_t *)prove_device(c, (const fe *)d_registers, width, length, ctx_depth, loop_depth, inputs16, n_inputs, outputs16,
+                                                n_outputs, *options, stats, 0.0f);
+    });
+}
+int dg_proof_serialized_len(const dg_proof_t *proof, size_t *len) {
+    return guarded([&] { DG_REQUIRE(proof && len, "null argument"); *len = ((const Proof *)proof)->bytes.size(); });
+}
+int dg_proof_serialize(const dg_proof_t *proof, uint8_t *buf, size_t cap) {
+    return guarded([&] {
+        DG_REQUIRE(proof && buf, "null argument");
+        const Proof *p = (const Proof *)proof;
+        DG_REQUIRE(cap >= p->bytes.size(), "buffer too small");
+        memcpy(buf, p->bytes.data(), p->bytes.size());
+    });
+}
+int dg_proof_digest(const dg_proof_t *proof, int which, uint8_t out32[32]) {
+    return guarded([&] {
+        DG_REQUIRE(proof && out32 && which >= 0 && which <= 2, "invalid argument");
+        const Proof *p = (const Proof *)proof;
+        memcpy(out32, which == 0 ? p->trace_root : which == 1 ? p->constraint_root : p->pow_seed, 32);
+    });
+}
+int dg_proof_pow_nonce(const dg_proof_t *proof, uint64_t *nonce) {
+    return guarded([&] { DG_REQUIRE(proof && nonce, "null argument"); *nonce = ((const Proof *)proof)->pow_nonce; });
+}
+void dg_proof_free(dg_proof_t *proof) { delete (Proof *)proof; }
+
+}  // extern "C"

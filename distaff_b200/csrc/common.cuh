@@ -1,0 +1,102 @@
+// Shared host-side plumbing for the CUDA prover: error handling, device buffers, the per-process context.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "fp128.cuh"
+
+namespace dg {
+
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define DG_CUDA(expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            throw dg::Error(-2, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+#define DG_REQUIRE(cond, msg)                                      \
+    do {                                                           \
+        if (!(cond)) throw dg::Error(-1, std::string(msg));        \
+    } while (0)
+
+// simple RAII device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t n) { alloc(n); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t n) {
+        release();
+        if (n == 0) return;
+        DG_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    void ensure(size_t n) { if (bytes < n) alloc(n); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+// two-level table of powers of a root of unity of order 2^log_order:
+//   w^e = hi[e >> lo_bits] * lo[e & (2^lo_bits - 1)]
+struct TwiddleTable {
+    DevBuf lo, hi;
+    int log_order = 0, lo_bits = 0;
+};
+struct TwiddleRef {
+    const fe *lo, *hi;
+    int lo_bits;
+    unsigned mask;    // order - 1
+};
+
+struct Context {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    // small root tables for the in-shared-memory transforms: roots[inv][l] = w_{2^l}^m, m < 2^(l-1), l = 1..MAX_LOG_L
+    DevBuf small_roots[2];
+    size_t small_root_offset[16];
+    std::map<int, TwiddleTable> twiddles;   // key = log_order * 2 + inverse
+    DevBuf ntt_tmp;                         // scratch of the multi-pass transforms
+    std::string last_error;
+
+    TwiddleRef twiddle(int log_order, bool inverse);
+    const fe *roots(int log_l, bool inverse) const { return small_roots[inverse ? 1 : 0].as<fe>() + small_root_offset[log_l]; }
+};
+
+Context &ctx();              // lazily initialised singleton (device 0 or $DG_DEVICE / dg_init)
+void ctx_init(int device);
+
+// host-side field helpers (portable path of fp128.cuh)
+fe host_root_of_unity(int log_order);            // w of order 2^log_order  (field::get_root_of_unity)
+fe host_pow(fe b, unsigned long long e);
+fe host_inv(fe a);
+
+static const int MAX_LOG_L = 10;                 // largest in-shared-memory transform: 1024 points
+
+// ---- NTT engine (ntt.cu) ------------------------------------------------------------------------------------------
+// natural-order DFT over the subgroup of order n = 2^log_n for `batch` vectors laid out with `stride` elements apart;
+// dst may equal src.  inverse: multiplies by n^-1 (polynom::interpolate_fft semantics).
+void ntt_batch(Context &c, const fe *src, fe *dst, int log_n, int batch, size_t src_stride, size_t dst_stride, bool inverse);
+// coset low-degree extension: coefficient vectors (batch of them, `coeff_len` = fold * n coefficients each, stride
+// `src_stride`) are evaluated over the 2^log_blowup cosets of the order-n subgroup; output per vector is
+// [coset c][k] = P(w_N^c * w_n^k), N = n << log_blowup, i.e. LDE index i = (k << log_blowup) + c lives at c*n + k.
+void lde_batch(Context &c, const fe *src, fe *dst, int log_n, int log_blowup, int fold, int batch, size_t src_stride, size_t dst_stride);
+
+}  // namespace dg

@@ -1,0 +1,104 @@
+// Per-process device context: stream, root-of-unity tables, scratch.  No CPU fallback exists: every entry point needs a
+// CUDA device and fails loudly (dg::Error -> negative return code + dg_last_error()) when there is none.
+#include "common.cuh"
+
+namespace dg {
+
+// 2^40-th root of unity G (/root/reference/src/math/field.rs:14)
+static const fe G40 = {0x86b8723e1920f4aaULL, 0x120532e7b364080aULL};
+
+fe host_pow(fe b, unsigned long long e) { return fe_pow_u64(b, e); }
+fe host_inv(fe a) { return fe_inv(a); }
+fe host_root_of_unity(int log_order) {
+    DG_REQUIRE(log_order >= 0 && log_order <= 40, "order cannot exceed 2^40");
+    fe r = G40;
+    for (int i = 0; i < 40 - log_order; i++) r = fe_sqr(r);
+    return r;
+}
+
+// out[i] = base^(i * step_pow)   where step = base^(2^shift) is passed precomputed
+__global__ void power_table_kernel(fe *out, fe step, unsigned count) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = fe_pow_u64(step, i);
+}
+
+static std::once_flag g_once;
+static Context *g_ctx = nullptr;
+static int g_device = -1;
+
+static void build_context(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw Error(-3, "no CUDA device available: distaff_b200 has no CPU path (cudaGetDeviceCount: " + std::string(cudaGetErrorString(e)) + ")");
+    DG_REQUIRE(device < count, "requested CUDA device does not exist");
+    DG_CUDA(cudaSetDevice(device));
+    Context *c = new Context();
+    c->device = device;
+    cudaDeviceProp prop;
+    DG_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    DG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // small root tables
+    size_t total = 0;
+    for (int l = 1; l <= MAX_LOG_L; l++) { c->small_root_offset[l] = total; total += (size_t)1 << (l - 1); }
+    c->small_root_offset[0] = 0;
+    for (int inv = 0; inv < 2; inv++) {
+        c->small_roots[inv].alloc(total * sizeof(fe));
+        for (int l = 1; l <= MAX_LOG_L; l++) {
+            fe w = host_root_of_unity(l);
+            if (inv) w = host_inv(w);
+            unsigned cnt = 1u << (l - 1);
+            power_table_kernel<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->small_roots[inv].as<fe>() + c->small_root_offset[l], w, cnt);
+            DG_CUDA(cudaGetLastError());
+        }
+    }
+    DG_CUDA(cudaStreamSynchronize(c->stream));
+    g_ctx = c;
+}
+
+void ctx_init(int device) {
+    std::call_once(g_once, [&]() {
+        if (device < 0) {
+            const char *env = getenv("DG_DEVICE");
+            device = env ? atoi(env) : 0;
+        }
+        g_device = device;
+        build_context(device);
+    });
+    if (!g_ctx) throw Error(-3, "CUDA context initialisation failed earlier in this process");
+    DG_CUDA(cudaSetDevice(g_ctx->device));
+}
+
+Context &ctx() {
+    ctx_init(-1);
+    return *g_ctx;
+}
+
+TwiddleRef Context::twiddle(int log_order, bool inverse) {
+    int key = log_order * 2 + (inverse ? 1 : 0);
+    auto it = twiddles.find(key);
+    if (it == twiddles.end()) {
+        TwiddleTable t;
+        t.log_order = log_order;
+        t.lo_bits = (log_order + 1) / 2;
+        unsigned lo_n = 1u << t.lo_bits, hi_n = 1u << (log_order - t.lo_bits);
+        fe w = host_root_of_unity(log_order);
+        if (inverse) w = host_inv(w);
+        fe whi = host_pow(w, lo_n);
+        t.lo.alloc(lo_n * sizeof(fe));
+        t.hi.alloc(hi_n * sizeof(fe));
+        power_table_kernel<<<(lo_n + 127) / 128, 128, 0, stream>>>(t.lo.as<fe>(), w, lo_n);
+        power_table_kernel<<<(hi_n + 127) / 128, 128, 0, stream>>>(t.hi.as<fe>(), whi, hi_n);
+        DG_CUDA(cudaGetLastError());
+        it = twiddles.emplace(key, std::move(t)).first;
+    }
+    TwiddleRef r;
+    r.lo = it->second.lo.as<fe>();
+    r.hi = it->second.hi.as<fe>();
+    r.lo_bits = it->second.lo_bits;
+    r.mask = log_order >= 32 ? 0xffffffffu : ((1u << log_order) - 1u);
+    return r;
+}
+
+}  // namespace dg

@@ -1,0 +1,285 @@
+// 128-bit prime field arithmetic for sm_100a, values kept canonical (< M) in two 64-bit registers.
+//
+//   M = 2^128 - 45*2^40 + 1          (/root/reference/src/math/field.rs:11)
+//   C = 2^128 mod M = 45*2^40 - 1    (a 46-bit constant)  =>  x*2^128 == x*C (mod M)
+//
+// The reference reduces with two 128x64 partial products (field.rs:38-73); here the full 256-bit product is formed with
+// 32-bit multiply-add chains (IMAD) and folded twice through C (Solinas-style), which maps onto the integer pipes of
+// the SM without any division.  Results are the canonical representatives, so every value is bit-identical to the
+// reference's `field::{add,sub,mul}` (checked against the oracle in tests/test_gpu_field.py).
+#pragma once
+#include <cstdint>
+
+namespace dg {
+
+struct __align__(16) fe {
+    unsigned long long lo, hi;
+};
+
+#define DG_M_LO 0xffffd30000000001ULL
+#define DG_M_HI 0xffffffffffffffffULL
+#define DG_C_LO 0x00002cffffffffffULL   // C = 45*2^40 - 1
+
+__host__ __device__ __forceinline__ fe fe_make(unsigned long long lo, unsigned long long hi = 0) { fe r; r.lo = lo; r.hi = hi; return r; }
+__host__ __device__ __forceinline__ bool fe_is_zero(fe a) { return (a.lo | a.hi) == 0; }
+__host__ __device__ __forceinline__ bool fe_eq(fe a, fe b) { return a.lo == b.lo && a.hi == b.hi; }
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// portable restatement of the same folding (plain C++): the host path (table setup, unit tests of the logic on the CPU
+// box) and the cross-check for the PTX path in tests/test_gpu_field.py
+// ---------------------------------------------------------------------------------------------------------------------
+namespace portable {
+
+typedef unsigned __int128 dg_u128;
+__host__ __device__ inline dg_u128 fe_to_u128(fe a) { return ((dg_u128)a.hi << 64) | a.lo; }
+__host__ __device__ inline fe fe_from_u128(dg_u128 v) { return fe_make((unsigned long long)v, (unsigned long long)(v >> 64)); }
+__host__ __device__ inline fe fe_add(fe a, fe b) {
+    dg_u128 x = fe_to_u128(a), y = fe_to_u128(b), s = x + y;
+    bool c1 = s < x;
+    dg_u128 t = s + DG_C_LO;
+    bool c2 = t < s;
+    return fe_from_u128((c1 || c2) ? t : s);
+}
+__host__ __device__ inline fe fe_sub(fe a, fe b) {
+    dg_u128 x = fe_to_u128(a), y = fe_to_u128(b), d = x - y;
+    return fe_from_u128(x < y ? d - DG_C_LO : d);
+}
+__host__ __device__ inline fe fe_neg(fe a) { return fe_sub(fe_make(0, 0), a); }
+__host__ __device__ inline fe fe_reduce256(unsigned long long t0, unsigned long long t1, unsigned long long t2, unsigned long long t3) {
+    dg_u128 p0 = (dg_u128)t2 * 45, p1 = (dg_u128)t3 * 45;
+    unsigned long long u0 = (unsigned long long)p0, p0h = (unsigned long long)(p0 >> 64), p1l = (unsigned long long)p1, p1h = (unsigned long long)(p1 >> 64);
+    unsigned long long u1 = p0h + p1l, u2 = p1h + (u1 < p1l ? 1ULL : 0ULL);
+    unsigned long long s0 = u0 << 40, s1 = (u1 << 40) | (u0 >> 24), s2 = (u2 << 40) | (u1 >> 24);
+    dg_u128 lo = ((dg_u128)t1 << 64) | t0, s = ((dg_u128)s1 << 64) | s0, hi = ((dg_u128)t3 << 64) | t2;
+    dg_u128 v = lo + s;
+    unsigned long long v2 = s2 + (v < lo ? 1ULL : 0ULL);
+    dg_u128 v_ = v - hi;
+    if (v < hi) v2 -= 1;
+    dg_u128 w = (dg_u128)v2 * DG_C_LO;
+    dg_u128 r = v_ + w;
+    bool cy = r < v_;
+    dg_u128 q = r + DG_C_LO;
+    bool cy2 = q < r;
+    return fe_from_u128((cy || cy2) ? q : r);
+}
+__host__ __device__ inline fe fe_mul(fe a, fe b) {
+    dg_u128 p00 = (dg_u128)a.lo * b.lo, p01 = (dg_u128)a.lo * b.hi, p10 = (dg_u128)a.hi * b.lo, p11 = (dg_u128)a.hi * b.hi;
+    dg_u128 mid = (p00 >> 64) + (unsigned long long)p01 + (unsigned long long)p10;
+    dg_u128 hi = p11 + (p01 >> 64) + (p10 >> 64) + (mid >> 64);
+    return fe_reduce256((unsigned long long)p00, (unsigned long long)mid, (unsigned long long)hi, (unsigned long long)(hi >> 64));
+}
+__host__ __device__ inline fe fe_sqr(fe a) { return fe_mul(a, a); }
+__host__ __device__ inline fe fe_pow_u128(fe a, unsigned long long e_lo, unsigned long long e_hi) {
+    fe r = fe_make(1, 0);
+    for (int i = 127; i >= 0; i--) {
+        r = fe_sqr(r);
+        unsigned long long bit = i >= 64 ? (e_hi >> (i - 64)) & 1ULL : (e_lo >> i) & 1ULL;
+        if (bit) r = fe_mul(r, a);
+    }
+    return r;
+}
+__host__ __device__ inline fe fe_pow_u64(fe a, unsigned long long e) { return fe_pow_u128(a, e, 0); }
+__host__ __device__ inline fe fe_inv(fe a) { return fe_pow_u128(a, DG_M_LO - 2ULL, DG_M_HI); }
+
+
+}  // namespace portable
+
+#ifdef __CUDA_ARCH__
+namespace ptx {
+
+__device__ __forceinline__ fe fe_add(fe a, fe b) {
+    unsigned long long s0, s1, t0, t1;
+    unsigned int c1, c2;
+    asm("{\n\t"
+        "add.cc.u64  %0, %6, %8;\n\t"
+        "addc.cc.u64 %1, %7, %9;\n\t"
+        "addc.u32    %4, 0, 0;\n\t"
+        "add.cc.u64  %2, %0, %10;\n\t"
+        "addc.cc.u64 %3, %1, 0;\n\t"
+        "addc.u32    %5, 0, 0;\n\t"
+        "}"
+        : "=&l"(s0), "=&l"(s1), "=&l"(t0), "=&l"(t1), "=&r"(c1), "=&r"(c2)
+        : "l"(a.lo), "l"(a.hi), "l"(b.lo), "l"(b.hi), "l"(DG_C_LO));
+    bool wrap = (c1 | c2) != 0;      // a + b >= M  <=>  a + b + C >= 2^128
+    fe r; r.lo = wrap ? t0 : s0; r.hi = wrap ? t1 : s1;
+    return r;
+}
+
+__device__ __forceinline__ fe fe_sub(fe a, fe b) {
+    unsigned long long d0, d1, t0, t1;
+    unsigned int bw;
+    asm("{\n\t"
+        "sub.cc.u64  %0, %5, %7;\n\t"
+        "subc.cc.u64 %1, %6, %8;\n\t"
+        "subc.u32    %4, 0, 0;\n\t"
+        "sub.cc.u64  %2, %0, %9;\n\t"
+        "subc.u64    %3, %1, 0;\n\t"
+        "}"
+        : "=&l"(d0), "=&l"(d1), "=&l"(t0), "=&l"(t1), "=&r"(bw)
+        : "l"(a.lo), "l"(a.hi), "l"(b.lo), "l"(b.hi), "l"(DG_C_LO));
+    fe r; r.lo = bw ? t0 : d0; r.hi = bw ? t1 : d1;   // a - b + M == a - b - C (mod 2^128)
+    return r;
+}
+
+__device__ __forceinline__ fe fe_neg(fe a) { return fe_sub(fe_make(0, 0), a); }
+
+// 256-bit product of two 128-bit values as eight 32-bit limbs (schoolbook, carry chains on the IMAD pipe)
+__device__ __forceinline__ void mul_wide_4x4(const unsigned int a[4], const unsigned int b[4], unsigned int r[8]) {
+    // row 0
+    asm("mul.lo.u32 %0, %4, %5;\n\t"
+        "mul.hi.u32 %1, %4, %5;\n\t"
+        "mul.lo.u32 %2, %4, %6;\n\t"   // placeholders overwritten below
+        "mul.hi.u32 %3, %4, %6;"
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]) : "r"(a[0]), "r"(b[0]), "r"(b[2]));
+    // r[0] = lo(a0 b0); r[1] = hi(a0 b0); r[2] = lo(a0 b2); r[3] = hi(a0 b2)
+    asm("mad.lo.cc.u32  %0, %4, %5, %0;\n\t"     // r1 += lo(a0 b1)
+        "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"     // r2 += hi(a0 b1) + c
+        "madc.lo.cc.u32 %2, %4, %6, %2;\n\t"     // r3 += lo(a0 b3) + c
+        "madc.hi.u32    %3, %4, %6, 0;"          // r4  = hi(a0 b3) + c
+        : "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "=&r"(r[4]) : "r"(a[0]), "r"(b[1]), "r"(b[3]));
+#pragma unroll
+    for (int i = 1; i < 4; i++) {
+        // even columns of row i: lo(ai b0)->r[i], hi(ai b0)->r[i+1], lo(ai b2)->r[i+2], hi(ai b2)->r[i+3], carry->r[i+4]
+        asm("mad.lo.cc.u32  %0, %5, %6, %0;\n\t"
+            "madc.hi.cc.u32 %1, %5, %6, %1;\n\t"
+            "madc.lo.cc.u32 %2, %5, %7, %2;\n\t"
+            "madc.hi.cc.u32 %3, %5, %7, %3;\n\t"
+            "addc.u32       %4, 0, 0;"
+            : "+r"(r[i]), "+r"(r[i + 1]), "+r"(r[i + 2]), "+r"(r[i + 3]), "=&r"(r[i + 4])
+            : "r"(a[i]), "r"(b[0]), "r"(b[2]));
+        // odd columns of row i: lo(ai b1)->r[i+1], hi(ai b1)->r[i+2], lo(ai b3)->r[i+3], hi(ai b3)->r[i+4]
+        asm("mad.lo.cc.u32  %0, %4, %5, %0;\n\t"
+            "madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+            "madc.lo.cc.u32 %2, %4, %6, %2;\n\t"
+            "madc.hi.u32    %3, %4, %6, %3;"
+            : "+r"(r[i + 1]), "+r"(r[i + 2]), "+r"(r[i + 3]), "+r"(r[i + 4])
+            : "r"(a[i]), "r"(b[1]), "r"(b[3]));
+    }
+}
+
+// reduce a 256-bit value (t0..t3 little-endian 64-bit limbs) modulo M
+__device__ __forceinline__ fe fe_reduce256(unsigned long long t0, unsigned long long t1, unsigned long long t2, unsigned long long t3) {
+    // fold 1: v = lo + hi*C = lo + ((hi*45) << 40) - hi         (hi = t3:t2, 128 bits)
+    // u = hi * 45  (134 bits: u2:u1:u0)
+    unsigned long long u0, u1, u2;
+    {
+        unsigned long long p0l = t2 * 45ULL, p0h = __umul64hi(t2, 45ULL);
+        unsigned long long p1l = t3 * 45ULL, p1h = __umul64hi(t3, 45ULL);
+        u0 = p0l;
+        u1 = p0h + p1l;                    // cannot lose a carry into u2 beyond what we add next
+        u2 = p1h + (u1 < p1l ? 1ULL : 0ULL);
+    }
+    // s = u << 40 (174 bits: s2:s1:s0)
+    unsigned long long s0 = u0 << 40;
+    unsigned long long s1 = (u1 << 40) | (u0 >> 24);
+    unsigned long long s2 = (u2 << 40) | (u1 >> 24);
+    // v = lo + s - hi   (192-bit arithmetic, result non-negative and < 2^175)
+    unsigned long long v0, v1, v2;
+    asm("{\n\t"
+        "add.cc.u64  %0, %3, %5;\n\t"
+        "addc.cc.u64 %1, %4, %6;\n\t"
+        "addc.u64    %2, %7, 0;\n\t"
+        "sub.cc.u64  %0, %0, %8;\n\t"
+        "subc.cc.u64 %1, %1, %9;\n\t"
+        "subc.u64    %2, %2, 0;\n\t"
+        "}"
+        : "=&l"(v0), "=&l"(v1), "=&l"(v2)
+        : "l"(t0), "l"(t1), "l"(s0), "l"(s1), "l"(s2), "l"(t2), "l"(t3));
+    // fold 2: w = v2 * C  (v2 < 2^47, C < 2^46 => w < 2^93)
+    unsigned long long w0 = v2 * DG_C_LO, w1 = __umul64hi(v2, DG_C_LO);
+    unsigned long long r0, r1, q0, q1;
+    unsigned int cy, cy2;
+    asm("{\n\t"
+        "add.cc.u64  %0, %6, %8;\n\t"
+        "addc.cc.u64 %1, %7, %9;\n\t"
+        "addc.u32    %4, 0, 0;\n\t"
+        "add.cc.u64  %2, %0, %10;\n\t"      // q = r + C  (used when r wrapped 2^128 or r >= M)
+        "addc.cc.u64 %3, %1, 0;\n\t"
+        "addc.u32    %5, 0, 0;\n\t"
+        "}"
+        : "=&l"(r0), "=&l"(r1), "=&l"(q0), "=&l"(q1), "=&r"(cy), "=&r"(cy2)
+        : "l"(v0), "l"(v1), "l"(w0), "l"(w1), "l"(DG_C_LO));
+    // if r wrapped (cy): true value = r + 2^128 == r + C (< M because r is tiny after a wrap)
+    // else if r >= M (cy2): r - M = r + C - 2^128 = q
+    bool use_q = (cy | cy2) != 0;
+    fe r; r.lo = use_q ? q0 : r0; r.hi = use_q ? q1 : r1;
+    return r;
+}
+
+__device__ __forceinline__ fe fe_mul(fe a, fe b) {
+    unsigned int x[4] = { (unsigned int)a.lo, (unsigned int)(a.lo >> 32), (unsigned int)a.hi, (unsigned int)(a.hi >> 32) };
+    unsigned int y[4] = { (unsigned int)b.lo, (unsigned int)(b.lo >> 32), (unsigned int)b.hi, (unsigned int)(b.hi >> 32) };
+    unsigned int r[8];
+    mul_wide_4x4(x, y, r);
+    return fe_reduce256(((unsigned long long)r[1] << 32) | r[0], ((unsigned long long)r[3] << 32) | r[2],
+                        ((unsigned long long)r[5] << 32) | r[4], ((unsigned long long)r[7] << 32) | r[6]);
+}
+
+__device__ __forceinline__ fe fe_sqr(fe a) { return fe_mul(a, a); }
+
+// multiply by a small constant (< 2^32)
+__device__ __forceinline__ fe fe_mul_small(fe a, unsigned int k) {
+    unsigned long long p0l = a.lo * (unsigned long long)k, p0h = __umul64hi(a.lo, (unsigned long long)k);
+    unsigned long long p1l = a.hi * (unsigned long long)k, p1h = __umul64hi(a.hi, (unsigned long long)k);
+    unsigned long long t1 = p0h + p1l;
+    unsigned long long t2 = p1h + (t1 < p1l ? 1ULL : 0ULL);
+    return fe_reduce256(p0l, t1, t2, 0ULL);
+}
+
+// a^e for a 64-bit exponent (square-and-multiply, MSB first)
+__device__ __forceinline__ fe fe_pow_u64(fe a, unsigned long long e) {
+    fe r = fe_make(1, 0);
+    if (e == 0) return r;
+    int top = 63 - __clzll((long long)e);
+    for (int i = top; i >= 0; i--) {
+        r = fe_sqr(r);
+        if ((e >> i) & 1ULL) r = fe_mul(r, a);
+    }
+    return r;
+}
+// a^e for a 128-bit exponent
+__device__ __forceinline__ fe fe_pow_u128(fe a, unsigned long long e_lo, unsigned long long e_hi) {
+    if (e_hi == 0) return fe_pow_u64(a, e_lo);
+    fe r = fe_pow_u64(a, e_hi);
+    for (int i = 63; i >= 0; i--) {
+        r = fe_sqr(r);
+        if ((e_lo >> i) & 1ULL) r = fe_mul(r, a);
+    }
+    return r;
+}
+// multiplicative inverse by Fermat (inv(0) = 0, as field::inv, field.rs:84)
+__device__ __forceinline__ fe fe_inv(fe a) { return fe_pow_u128(a, DG_M_LO - 2ULL, DG_M_HI); }
+
+__device__ __forceinline__ fe fe_cube(fe a) { return fe_mul(fe_sqr(a), a); }
+
+
+}  // namespace ptx
+#endif
+
+// ---- public entry points: PTX path on the device, portable path on the host ------------------------------------------
+#ifdef __CUDA_ARCH__
+#define DG_IMPL ptx
+#else
+#define DG_IMPL portable
+#endif
+__host__ __device__ __forceinline__ fe fe_add(fe a, fe b) { return DG_IMPL::fe_add(a, b); }
+__host__ __device__ __forceinline__ fe fe_sub(fe a, fe b) { return DG_IMPL::fe_sub(a, b); }
+__host__ __device__ __forceinline__ fe fe_neg(fe a) { return DG_IMPL::fe_neg(a); }
+__host__ __device__ __forceinline__ fe fe_mul(fe a, fe b) { return DG_IMPL::fe_mul(a, b); }
+__host__ __device__ __forceinline__ fe fe_sqr(fe a) { return DG_IMPL::fe_sqr(a); }
+__host__ __device__ __forceinline__ fe fe_pow_u64(fe a, unsigned long long e) { return DG_IMPL::fe_pow_u64(a, e); }
+__host__ __device__ __forceinline__ fe fe_pow_u128(fe a, unsigned long long lo, unsigned long long hi) { return DG_IMPL::fe_pow_u128(a, lo, hi); }
+__host__ __device__ __forceinline__ fe fe_inv(fe a) { return DG_IMPL::fe_inv(a); }
+__host__ __device__ __forceinline__ fe fe_cube(fe a) { return fe_mul(fe_sqr(a), a); }
+__host__ __device__ __forceinline__ fe fe_mul_small(fe a, unsigned int k) {
+#ifdef __CUDA_ARCH__
+    return ptx::fe_mul_small(a, k);
+#else
+    return portable::fe_mul(a, fe_make(k, 0));
+#endif
+}
+#undef DG_IMPL
+
+
+}  // namespace dg

@@ -1,0 +1,273 @@
+// Batched radix-2 NTT / inverse NTT and coset low-degree extension over F_M for sm_100a.
+//
+// Replaces, for the prove hot path, the reference's recursive in-place FFT + bit-reversal permutation
+//   /root/reference/src/math/fft.rs:16-79, /root/reference/src/math/polynom.rs:34-41,93-103
+// and the zero-padded extension loop of /root/reference/src/stark/trace/trace_table.rs:143-169.
+// Contract (pinned by fft.rs:117-157): natural-order input -> natural-order DFT  X[k] = sum_j x[j] w^(jk).
+//
+// Design: a transform of size n = 2^log_n is split into at most three passes of <= 1024-point sub-transforms that run
+// entirely in shared memory (decimation in frequency, twiddles for the in-block stages staged in shared memory).  Every
+// pass streams HBM once with 16-byte vector accesses; a block owns a tile of T neighbouring "lanes" (independent
+// sub-transforms whose elements are adjacent in memory) so that global reads and writes are T*16-byte contiguous
+// segments.  Inter-pass twiddles w^(lane*k) come from a two-level power table (2 loads + 1 multiply).
+//
+// Low-degree extension does not zero-pad: evaluating P (n coefficients) on the LDE domain of size N = b*n is done as b
+// independent size-n transforms of the coset-scaled coefficients p[m] * w_N^(c*m); the result is stored coset-major
+// ([c][k] <-> LDE index b*k + c), which is the layout every later kernel (leaf hashing, constraint evaluation, FRI)
+// consumes with unit-stride reads.  This removes log2(b) of the log2(N) butterfly levels and all work on zeros.
+#include "common.cuh"
+
+namespace dg {
+
+struct PassGeom {
+    int log_t;                          // lanes per block (power of two)
+    unsigned num_tiles;                 // blockIdx.x = outer * num_tiles + tile
+    long long in_outer, in_lane, in_point;
+    long long out_outer, out_lane, out_point;
+    long long in_batch_y, out_batch_y, in_batch_z, out_batch_z;
+    int lane_major;                     // shared-memory layout: 0 = [point][lane], 1 = [lane][point] (padded)
+    int tw_on;                          // multiply output k of lane (tile*T+lane) by tw^((tile*T+lane)*k)
+    TwiddleRef tw;
+    int has_scale;
+    fe scale;
+    int coset_on;                       // input transform of the LDE: sum_f src[j + f*fold_stride] * cw^(c*(j + f*fold_stride))
+    int fold;
+    long long fold_stride;
+    TwiddleRef cw;
+    const fe *roots;                    // w_L^m, m < L/2
+};
+
+__device__ __forceinline__ fe tw_lookup(const TwiddleRef &t, unsigned long long e) {
+    unsigned ee = (unsigned)e & t.mask;
+    fe a = t.lo[ee & ((1u << t.lo_bits) - 1u)];
+    fe b = t.hi[ee >> t.lo_bits];
+    return fe_mul(a, b);
+}
+
+template <int LOG_L>
+__global__ void __launch_bounds__(256) ntt_pass_kernel(const fe *__restrict__ src, fe *__restrict__ dst, const PassGeom g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int L = 1 << LOG_L;
+    fe *s_roots = reinterpret_cast<fe *>(smem_raw);
+    fe *s = s_roots + (L / 2 > 0 ? L / 2 : 1);
+    const int T = 1 << g.log_t;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const unsigned tile = blockIdx.x % g.num_tiles, outer = blockIdx.x / g.num_tiles;
+    const long long in_base = (long long)outer * g.in_outer + (long long)tile * T * g.in_lane;   // index inside the vector
+    src += (long long)blockIdx.y * g.in_batch_y + (long long)blockIdx.z * g.in_batch_z;
+    dst += (long long)blockIdx.y * g.out_batch_y + (long long)blockIdx.z * g.out_batch_z + (long long)outer * g.out_outer +
+           (long long)tile * T * g.out_lane;
+    const int ps = g.lane_major ? 1 : T;
+    const int ls = g.lane_major ? (L + 1) : 1;
+
+    for (int i = tid; i < L / 2; i += nthreads) s_roots[i] = g.roots[i];
+
+    // ---- load tile (optionally applying the coset transform of the LDE)
+    for (int e = tid; e < L * T; e += nthreads) {
+        int t, p;
+        if (g.lane_major) { p = e & (L - 1); t = e >> LOG_L; }
+        else { t = e & (T - 1); p = e >> g.log_t; }
+        long long j = in_base + (long long)t * g.in_lane + (long long)p * g.in_point;
+        fe v;
+        if (g.coset_on) {
+            const unsigned long long c = blockIdx.y;
+            v = fe_make(0, 0);
+            for (int f = 0; f < g.fold; f++) {
+                long long jj = j + (long long)f * g.fold_stride;
+                fe x = src[jj];
+                v = fe_add(v, fe_mul(x, tw_lookup(g.cw, c * (unsigned long long)jj)));
+            }
+        } else {
+            v = src[j];
+        }
+        s[p * ps + t * ls] = v;
+    }
+    __syncthreads();
+
+    // ---- L-point decimation-in-frequency transform per lane (natural in, bit-reversed out)
+#pragma unroll 1
+    for (int st = 0; st < LOG_L; st++) {
+        const int half = L >> (st + 1);
+        for (int b = tid; b < (L / 2) * T; b += nthreads) {
+            int t, q;
+            if (g.lane_major) { q = b & (L / 2 - 1); t = b >> (LOG_L - 1); }
+            else { t = b & (T - 1); q = b >> g.log_t; }
+            const int j = q & (half - 1);
+            const int i0 = ((q - j) << 1) + j;
+            fe *p0 = s + i0 * ps + t * ls;
+            fe *p1 = p0 + half * ps;
+            fe a = *p0, bb = *p1;
+            *p0 = fe_add(a, bb);
+            fe d = fe_sub(a, bb);
+            if (half > 1) d = fe_mul(d, s_roots[j << st]);
+            *p1 = d;
+        }
+        __syncthreads();
+    }
+
+    // ---- store: position q holds X[bitrev(q)]
+    for (int e = tid; e < L * T; e += nthreads) {
+        const int t = e & (T - 1), q = e >> g.log_t;
+        const unsigned k = LOG_L == 0 ? 0u : (__brev((unsigned)q) >> (32 - (LOG_L == 0 ? 1 : LOG_L)));
+        fe v = s[q * ps + t * ls];
+        if (g.tw_on) v = fe_mul(v, tw_lookup(g.tw, (unsigned long long)(tile * T + t) * k));
+        if (g.has_scale) v = fe_mul(v, g.scale);
+        dst[(long long)t * g.out_lane + (long long)k * g.out_point] = v;
+    }
+}
+
+typedef void (*PassKernel)(const fe *, fe *, const PassGeom);
+static PassKernel pass_kernel(int log_l) {
+    switch (log_l) {
+        case 1: return ntt_pass_kernel<1>;  case 2: return ntt_pass_kernel<2>;  case 3: return ntt_pass_kernel<3>;
+        case 4: return ntt_pass_kernel<4>;  case 5: return ntt_pass_kernel<5>;  case 6: return ntt_pass_kernel<6>;
+        case 7: return ntt_pass_kernel<7>;  case 8: return ntt_pass_kernel<8>;  case 9: return ntt_pass_kernel<9>;
+        case 10: return ntt_pass_kernel<10>;
+    }
+    throw Error(-1, "unsupported sub-transform size");
+}
+
+static void launch_pass(Context &c, int log_l, PassGeom g, const fe *src, fe *dst, unsigned blocks_x, unsigned by, unsigned bz) {
+    const int L = 1 << log_l, T = 1 << g.log_t;
+    size_t smem = (size_t)(L / 2 > 0 ? L / 2 : 1) * sizeof(fe) + (size_t)(g.lane_major ? T * (L + 1) : L * T) * sizeof(fe);
+    int threads = L * T / 2;
+    if (threads > 256) threads = 256;
+    if (threads < 32) threads = 32;
+    PassKernel k = pass_kernel(log_l);
+    static bool attr_set[MAX_LOG_L + 1] = {false};
+    if (!attr_set[log_l]) {
+        DG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set[log_l] = true;
+    }
+    DG_REQUIRE(by <= 65535 && bz <= 65535, "batch too large for one launch");
+    k<<<dim3(blocks_x, by, bz), threads, smem, c.stream>>>(src, dst, g);
+    DG_CUDA(cudaGetLastError());
+}
+
+static int lanes_log(int log_l, long long available) {
+    int lt = 4;                                   // 16 lanes
+    while ((1 << (log_l + lt)) > 4096 && lt > 0) lt--;    // keep tiles at 4096 elements = 64 KB
+    while ((1LL << lt) > available && lt > 0) lt--;
+    return lt;
+}
+
+// split log_n into 1..3 pass sizes (outermost first)
+static int split_passes(int log_n, int l[3]) {
+    if (log_n <= MAX_LOG_L) { l[0] = log_n; return 1; }
+    if (log_n <= 2 * MAX_LOG_L) { l[0] = (log_n + 1) / 2; l[1] = log_n / 2; return 2; }
+    DG_REQUIRE(log_n <= 3 * MAX_LOG_L, "transform too large");
+    l[0] = (log_n + 2) / 3; l[1] = (log_n + 1) / 3; l[2] = log_n / 3;
+    return 3;
+}
+
+struct CosetSpec { bool on; int log_blowup; int fold; };
+
+// Runs the passes of one batched transform.  `by` = number of y-batches (cosets for the LDE, else 1), `bz` = vectors.
+// src strides: vector stride src_stride (z), y stride 0 for the LDE (every coset reads the same coefficients).
+static void run_transform(Context &c, const fe *src, fe *dst, int log_n, bool inverse, unsigned by, unsigned bz, long long src_stride_z,
+                          long long dst_stride_y, long long dst_stride_z, CosetSpec cs) {
+    int l[3];
+    const int np = split_passes(log_n, l);
+    const long long n = 1LL << log_n;
+    fe scale = fe_make(1, 0);
+    if (inverse) scale = host_inv(fe_make((unsigned long long)n, 0));
+
+    PassGeom base;
+    memset(&base, 0, sizeof base);
+    if (cs.on) {
+        base.coset_on = 1;
+        base.fold = cs.fold;
+        base.fold_stride = n;
+        base.cw = c.twiddle(log_n + cs.log_blowup, false);
+    }
+
+    fe *tmp = nullptr;
+    long long tmp_stride_y = n, tmp_stride_z = n * by;
+    if (np > 1) {
+        c.ntt_tmp.ensure((size_t)n * by * bz * sizeof(fe));
+        tmp = c.ntt_tmp.as<fe>();
+    }
+
+    if (np == 1) {
+        PassGeom g = base;
+        g.log_t = 0; g.num_tiles = 1;
+        g.in_point = 1; g.out_point = 1; g.in_lane = 0; g.out_lane = 0;
+        g.in_batch_y = 0; g.in_batch_z = src_stride_z; g.out_batch_y = dst_stride_y; g.out_batch_z = dst_stride_z;
+        g.lane_major = 1; g.tw_on = 0;
+        g.has_scale = inverse; g.scale = scale;
+        g.roots = c.roots(l[0], inverse);
+        launch_pass(c, l[0], g, src, dst, 1, by, bz);
+        return;
+    }
+
+    const long long N1 = 1LL << l[0];
+    const long long R1 = n >> l[0];
+    {   // pass 1: N1-point transforms over j1 (stride R1), twiddle w_n^(j' * k1)
+        PassGeom g = base;
+        g.log_t = lanes_log(l[0], R1);
+        g.num_tiles = (unsigned)(R1 >> g.log_t);
+        g.in_point = R1; g.in_lane = 1; g.out_point = R1; g.out_lane = 1;
+        g.in_batch_y = 0; g.in_batch_z = src_stride_z; g.out_batch_y = tmp_stride_y; g.out_batch_z = tmp_stride_z;
+        g.lane_major = 0;
+        g.tw_on = 1; g.tw = c.twiddle(log_n, inverse);
+        g.roots = c.roots(l[0], inverse);
+        launch_pass(c, l[0], g, src, tmp, g.num_tiles, by, bz);
+    }
+    long long N2 = 1;
+    if (np == 3) {   // pass 2: within every row k1, N2-point transforms over ja (stride N3), twiddle w_R1^(jb * ka)
+        N2 = 1LL << l[1];
+        const long long N3 = 1LL << l[2];
+        PassGeom g;
+        memset(&g, 0, sizeof g);
+        g.log_t = lanes_log(l[1], N3);
+        g.num_tiles = (unsigned)(N3 >> g.log_t);
+        g.in_point = N3; g.in_lane = 1; g.in_outer = R1; g.out_point = N3; g.out_lane = 1; g.out_outer = R1;
+        g.in_batch_y = tmp_stride_y; g.in_batch_z = tmp_stride_z; g.out_batch_y = tmp_stride_y; g.out_batch_z = tmp_stride_z;
+        g.lane_major = 0;
+        g.tw_on = 1; g.tw = c.twiddle(log_n - l[0], inverse);
+        g.roots = c.roots(l[1], inverse);
+        launch_pass(c, l[1], g, tmp, tmp, (unsigned)(g.num_tiles * N1), by, bz);
+    }
+    {   // last pass: contiguous NL-point transforms; output index k1 + N1*ka + N1*N2*kb
+        const int ll = l[np - 1];
+        PassGeom g;
+        memset(&g, 0, sizeof g);
+        g.log_t = lanes_log(ll, N1);
+        g.num_tiles = (unsigned)(N1 >> g.log_t);
+        g.in_point = 1; g.in_lane = R1; g.in_outer = (np == 3) ? (1LL << ll) : 0;
+        g.out_lane = 1; g.out_outer = (np == 3) ? N1 : 0; g.out_point = N1 * N2;
+        g.in_batch_y = tmp_stride_y; g.in_batch_z = tmp_stride_z; g.out_batch_y = dst_stride_y; g.out_batch_z = dst_stride_z;
+        g.lane_major = 1; g.tw_on = 0;
+        g.has_scale = inverse; g.scale = scale;
+        g.roots = c.roots(ll, inverse);
+        launch_pass(c, ll, g, tmp, dst, (unsigned)(g.num_tiles * N2), by, bz);
+    }
+}
+
+void ntt_batch(Context &c, const fe *src, fe *dst, int log_n, int batch, size_t src_stride, size_t dst_stride, bool inverse) {
+    DG_REQUIRE(log_n >= 1 && log_n <= 30, "log_n out of range");
+    const size_t n = (size_t)1 << log_n;
+    // bound the scratch: process vectors in chunks of at most ~1 GiB of scratch
+    size_t max_chunk = std::max<size_t>(1, ((size_t)1 << 30) / (n * sizeof(fe)));
+    if (max_chunk > 65535) max_chunk = 65535;
+    for (size_t b0 = 0; b0 < (size_t)batch; b0 += max_chunk) {
+        size_t nb = std::min(max_chunk, (size_t)batch - b0);
+        run_transform(c, src + b0 * src_stride, dst + b0 * dst_stride, log_n, inverse, 1, (unsigned)nb, (long long)src_stride, 0,
+                      (long long)dst_stride, CosetSpec{false, 0, 1});
+    }
+}
+
+void lde_batch(Context &c, const fe *src, fe *dst, int log_n, int log_blowup, int fold, int batch, size_t src_stride, size_t dst_stride) {
+    DG_REQUIRE(log_n >= 1 && log_n + log_blowup <= 30, "LDE domain too large");
+    const size_t n = (size_t)1 << log_n;
+    const unsigned cosets = 1u << log_blowup;
+    size_t max_chunk = std::max<size_t>(1, ((size_t)1 << 30) / (n * cosets * sizeof(fe)));
+    if (max_chunk > 65535) max_chunk = 65535;
+    for (size_t b0 = 0; b0 < (size_t)batch; b0 += max_chunk) {
+        size_t nb = std::min(max_chunk, (size_t)batch - b0);
+        run_transform(c, src + b0 * src_stride, dst + b0 * dst_stride, log_n, false, cosets, (unsigned)nb, (long long)src_stride,
+                      (long long)n, (long long)dst_stride, CosetSpec{true, log_blowup, fold});
+    }
+}
+
+}  // namespace dg

@@ -1,0 +1,112 @@
+/* distaff_gpu.h -- C-ABI of the B200 (sm_100a) STARK prover backend for Distaff.
+ *
+ * The reference has no FFI seam; the seam this library replaces is the single call
+ *     stark::prove(&mut trace, inputs, outputs, options) -> StarkProof
+ * at /root/reference/src/lib.rs:62  (definition: /root/reference/src/stark/prover.rs:17-169).
+ * INTEGRATION.md shows the Rust binding (extern "C" block + replacement body of prover.rs::prove).
+ *
+ * Conventions
+ *   - field elements are 16 little-endian bytes (a Rust u128, /root/reference/src/utils/mod.rs:35-41), canonical < M;
+ *   - digests are 32 bytes; all sizes are in elements unless a name says bytes;
+ *   - every function returns 0 on success and a negative code on failure; dg_last_error() describes the failure;
+ *     nothing unwinds across the boundary;  there is NO CPU fallback: without a CUDA device every call fails with -3;
+ *   - the caller owns input buffers (read-only for the duration of the call) and output buffers it passes in;
+ *     objects returned through dg_proof_t** are owned by the library until dg_proof_free();
+ *   - calls are serialised internally (one context per process, one device: $DG_DEVICE or dg_init()).
+ */
+#ifndef DISTAFF_GPU_H
+#define DISTAFF_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DG_OK 0
+#define DG_ERR_INVALID (-1)      /* bad argument (mirrors the reference's assert!s, e.g. trace_table.rs:23-58, options.rs:29-50) */
+#define DG_ERR_CUDA (-2)         /* CUDA runtime failure */
+#define DG_ERR_NO_DEVICE (-3)    /* no CUDA device: this backend has no CPU path */
+#define DG_ERR_EXHAUSTED (-4)    /* PoW / query-position search exhausted (utils/mod.rs:39-41 panics in the reference) */
+#define DG_ERR_UNSATISFIED (-5)  /* transition constraints do not vanish on the trace (evaluator.rs:152-157 panics) */
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------- */
+int dg_init(int device);                     /* optional; device < 0 = $DG_DEVICE or 0 */
+const char *dg_last_error(void);             /* thread-local message of the last failing call */
+int dg_device_info(char *name, size_t cap, int *sm_count, size_t *total_mem);
+
+/* ---- the hot path: replaces stark::prove (prover.rs:17) ----------------------------------------------------------- */
+typedef struct {
+    const uint8_t *const *columns; /* width pointers, each to length*16 bytes: register traces, column-major (trace_table.rs:10) */
+    uint32_t width;                /* 15 + ctx_depth + loop_depth + stack_depth (trace_state.rs:115-118)                    */
+    uint64_t length;               /* trace length n, power of two >= 16                                                    */
+    uint32_t ctx_depth, loop_depth;/* as returned by processor::execute (processor/mod.rs:23-46)                            */
+} dg_trace_t;
+
+typedef struct {                   /* ProofOptions (options.rs:16-23) */
+    uint32_t extension_factor;     /* 16..256, power of two (default 32) */
+    uint32_t num_queries;          /* 1..128 (default 50)                */
+    uint32_t grinding_factor;      /* 0..32 (default 20)                 */
+    uint32_t hash_id;              /* 0 = blake3 (the only serialisable hash, options.rs:107) */
+} dg_options_t;
+
+typedef struct dg_proof dg_proof_t;
+
+typedef struct {                   /* per-stage device time in ms, the nine steps of prover.rs:19-167 */
+    float stage_ms[9];
+    float h2d_ms, total_ms;
+    uint64_t kernel_launches;
+} dg_prove_stats_t;
+
+int dg_prove(const dg_trace_t *trace, const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs,
+             const dg_options_t *options, dg_proof_t **proof_out, dg_prove_stats_t *stats /* may be NULL */);
+/* same, with the register traces already resident in device memory: one allocation of width*length*16 bytes, column-major */
+int dg_prove_device(const void *d_registers, uint32_t width, uint64_t length, uint32_t ctx_depth, uint32_t loop_depth,
+                    const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs,
+                    const dg_options_t *options, dg_proof_t **proof_out, dg_prove_stats_t *stats);
+
+/* bincode 1.3.1 encoding of StarkProof (proof.rs:10-37), what main.rs:45 serialises */
+int dg_proof_serialized_len(const dg_proof_t *proof, size_t *len);
+int dg_proof_serialize(const dg_proof_t *proof, uint8_t *buf, size_t cap);
+/* intermediate commitments, for differential tests: which = 0 trace root, 1 constraint root, 2 PoW seed */
+int dg_proof_digest(const dg_proof_t *proof, int which, uint8_t out32[32]);
+int dg_proof_pow_nonce(const dg_proof_t *proof, uint64_t *nonce);
+void dg_proof_free(dg_proof_t *proof);
+
+/* ---- building blocks (micro-benchmarks of BASELINE.json config 5; same kernels the prover uses) ---------------------- */
+/* math::fft / polynom::{eval_fft, interpolate_fft} (polynom.rs:23-28,82-86): natural-order DFT of `batch` vectors of 2^log_n
+ * elements, in place in host memory */
+int dg_ntt(uint8_t *values, uint32_t log_n, uint32_t batch, int inverse);
+/* TraceTable::extend (trace_table.rs:143-169) for `batch` columns: n values in, n*blowup evaluations out in LOGICAL order
+ * (out[i] = P(w_N^i)), host memory */
+int dg_lde(const uint8_t *values, uint8_t *extended, uint32_t log_n, uint32_t log_blowup, uint32_t batch);
+/* crypto::build_merkle_nodes (merkle.rs:269-294) with blake3: n_leaves*32 bytes in, n_leaves*32 bytes of nodes out */
+int dg_merkle_build(const uint8_t *leaves, uint64_t n_leaves, uint8_t *nodes);
+/* TraceTable::build_merkle_tree leaf step (trace_table.rs:176-183): hashes the rows of a column-major width x rows matrix */
+int dg_hash_rows(const uint8_t *columns, uint32_t width, uint64_t rows, uint8_t *digests);
+/* utils::find_pow_nonce (proof_of_work.rs:4-32) */
+int dg_find_pow_nonce(const uint8_t seed[32], uint32_t grinding_factor, uint64_t *nonce, uint8_t new_seed[32]);
+/* element-wise field ops on vectors (op: 0 add, 1 sub, 2 mul, 3 inv, 4 exp(a, b)), for differential tests of the arithmetic;
+ * impl: 0 = PTX path used by the kernels, 1 = portable C++ path */
+int dg_field_op(int op, int impl, const uint8_t *a, const uint8_t *b, uint8_t *out, uint64_t n);
+
+/* ---- device-resident variants (timed with CUDA events on the library's stream; *ms may be NULL) ----------------------- */
+int dg_dev_alloc(void **ptr, size_t bytes);
+int dg_dev_free(void *ptr);
+int dg_dev_upload(void *dst, const void *src, size_t bytes);
+int dg_dev_download(void *dst, const void *src, size_t bytes);
+int dg_dev_sync(void);
+int dg_dev_ntt(void *d_values, uint32_t log_n, uint32_t batch, int inverse, float *ms);
+/* d_polys: batch x n coefficients; d_ext: batch x (n << log_blowup) evaluations, coset-major ([c][k] = LDE index k*blowup + c) */
+int dg_dev_lde(const void *d_polys, void *d_ext, uint32_t log_n, uint32_t log_blowup, uint32_t batch, float *ms);
+int dg_dev_merkle_build(const void *d_leaves, uint64_t n_leaves, void *d_nodes, float *ms);
+/* d_ext coset-major as produced by dg_dev_lde; d_leaves: (n << log_blowup) digests in logical row order */
+int dg_dev_hash_rows(const void *d_ext, uint32_t width, uint32_t log_n, uint32_t log_blowup, void *d_leaves, float *ms);
+/* writes > L2-size scratch to evict the L2 between timed iterations */
+int dg_dev_flush_l2(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISTAFF_GPU_H */

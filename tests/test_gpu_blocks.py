@@ -1,0 +1,117 @@
+"""-m gpu parity tests of the CUDA building blocks against the CPU oracle, through the C-ABI (distaff_b200.api).
+Bit-exact: everything here is integer / byte work."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+M = 2**128 - 45 * 2**40 + 1
+
+
+@pytest.fixture(scope="module")
+def dg():
+    import distaff_b200
+    from distaff_b200 import backend
+    info = backend.device_info()          # fails loudly without a GPU / without the built .so
+    assert info["sm_count"] > 0
+    return distaff_b200
+
+
+def _rand(n, seed):
+    from distaff_b200 import felt
+    return felt.random_elements(n, seed)
+
+
+EDGE = [0, 1, 2, M - 1, M - 2, 2**64 - 1, 2**64, 2**64 + 1, 2**127, (M + 1) // 2, 45 * 2**40 - 1, 45 * 2**40, 2**128 - 2**88, M - 2**64]
+
+
+def test_field_ops_ptx_and_portable_match_oracle(dg, po):
+    from distaff_b200 import felt
+    a_int = [x for x in EDGE for _ in EDGE] + felt.to_ints(_rand(4000, 1))
+    b_int = [y for _ in EDGE for y in EDGE] + felt.to_ints(_rand(4000, 2))
+    a, b = felt.from_ints(a_int), felt.from_ints(b_int)
+    for op, f in (("add", lambda x, y: (x + y) % M), ("sub", lambda x, y: (x - y) % M), ("mul", lambda x, y: x * y % M)):
+        want = [f(x, y) for x, y in zip(a_int, b_int)]
+        for impl in (0, 1):
+            assert felt.to_ints(dg.field_op(op, a, b, impl=impl)) == want, (op, impl)
+    sub = felt.from_ints(a_int[:300])
+    want = [pow(x, M - 2, M) if x else 0 for x in a_int[:300]]
+    assert felt.to_ints(dg.field_op("inv", sub, impl=0)) == want
+    e = felt.from_ints(b_int[:300])
+    want = [pow(x, y, M) if x else 0 for x, y in zip(a_int[:300], b_int[:300])]
+    assert felt.to_ints(dg.field_op("exp", sub, e, impl=0)) == want
+    # spot-check against the oracle's limb-for-limb restatement of field.rs::mul
+    for x, y in list(zip(a_int, b_int))[:400]:
+        assert po.field_op("mul", x, y) == x * y % M
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 8, 10, 11, 12, 13, 16, 19, 20, 21, 22])
+def test_ntt_matches_oracle(dg, po, log_n):
+    n = 1 << log_n
+    batch = 3 if log_n <= 16 else 1
+    x = _rand(n * batch, 100 + log_n).reshape(batch, n, 2)
+    y = dg.ntt(x)
+    for b in range(batch):
+        assert np.array_equal(y[b], po.fft(x[b])), (log_n, b)
+    back = dg.intt(y)
+    assert np.array_equal(back, x)
+
+
+def test_ntt_edge_inputs(dg, po):
+    from distaff_b200 import felt
+    n = 1 << 12
+    for vec in ([0] * n, [M - 1] * n, [1] + [0] * (n - 1), list(range(n))):
+        x = felt.from_ints(vec)
+        assert np.array_equal(dg.ntt(x), po.fft(x))
+        assert np.array_equal(dg.intt(x), po.fft(x, inverse=True))
+
+
+@pytest.mark.parametrize("log_n,blowup", [(4, 16), (4, 32), (8, 32), (10, 32), (11, 32), (13, 32), (16, 32), (12, 64)])
+def test_lde_matches_reference_extension(dg, po, log_n, blowup):
+    # TraceTable::extend: interpolate (iNTT n), zero-pad to N, evaluate (NTT N)   trace_table.rs:143-169
+    n = 1 << log_n
+    batch = 3 if log_n <= 13 else 2
+    x = _rand(n * batch, 200 + log_n).reshape(batch, n, 2)
+    got = dg.lde(x, blowup)
+    for b in range(batch):
+        poly = po.fft(x[b], inverse=True)
+        padded = np.zeros((n * blowup, 2), dtype=np.uint64)
+        padded[:n] = poly
+        want = po.fft(padded)
+        assert np.array_equal(got[b], want), (log_n, b)
+        assert np.array_equal(got[b, ::blowup], x[b])        # the extension agrees with the trace on the trace domain
+
+
+@pytest.mark.parametrize("w", [1, 3, 4, 5, 16, 17, 20, 26, 63, 64, 65, 100, 127])
+def test_row_hashing_matches_blake3(dg, po, w):
+    rows = 257
+    cols = _rand(w * rows, 300 + w).reshape(w, rows, 2)
+    got = dg.hash_rows(cols)
+    for r in (0, 1, 17, 255, 256):
+        row_bytes = cols[:, r, :].tobytes()
+        assert got[32 * r:32 * r + 32] == po.hash("blake3", row_bytes), (w, r)
+
+
+@pytest.mark.parametrize("log_l", [1, 2, 3, 5, 10, 11, 12, 16])
+def test_merkle_nodes_match_oracle(dg, po, log_l):
+    n = 1 << log_l
+    leaves = np.random.Generator(np.random.PCG64(log_l)).integers(0, 256, size=n * 32, dtype=np.uint8).tobytes()
+    assert dg.merkle_build(leaves) == po.merkle_nodes("blake3", leaves)
+
+
+def test_pow_nonce_is_the_smallest(dg, po):
+    import ctypes
+    for g, seed_byte in ((0, 1), (8, 2), (12, 3), (16, 4), (20, 5)):
+        seed = bytes([seed_byte] * 32)
+        new_seed, nonce = dg.find_pow_nonce(seed, g)
+        out = ctypes.create_string_buffer(32)
+        want = po.lib().or_find_pow_nonce(seed, g, out)
+        assert nonce == want and new_seed == out.raw, g
+
+
+def test_invalid_arguments_return_errors(dg):
+    from distaff_b200 import backend
+    with pytest.raises(backend.DgError):
+        dg.merkle_build(b"\0" * 96)                      # 3 leaves: not a power of two (merkle.rs:26)
+    with pytest.raises(backend.DgError):
+        dg.find_pow_nonce(b"\0" * 32, 33)                # options.rs:43
