@@ -75,6 +75,7 @@ struct Context {
     std::map<int, TwiddleTable> twiddles;   // key = log_order * 2 + inverse
     DevBuf ntt_tmp;                         // scratch of the multi-pass transforms
     std::string last_error;
+    unsigned long long launches = 0;        // kernels launched by this library (bench.py's gpu_launches)
 
     TwiddleRef twiddle(int log_order, bool inverse);
     const fe *roots(int log_l, bool inverse) const { return small_roots[inverse ? 1 : 0].as<fe>() + small_root_offset[log_l]; }

@@ -1,0 +1,90 @@
+// FRI layer kernels: row hashing and radix-4 folding.
+//
+//   fri::reduce                 /root/reference/src/stark/fri/prover.rs:11-53
+//   quartic::transpose          /root/reference/src/math/quartic.rs:137-152   (rows r: v[r], v[r+R], v[r+2R], v[r+3R])
+//   quartic::interpolate_batch  /root/reference/src/math/quartic.rs:37-135    (cubic through 4 points, batch inversion)
+//   quartic::evaluate_batch     /root/reference/src/math/quartic.rs:20-31
+//
+// The reference interpolates every row with Lagrange formulas and one global batch inversion.  Because the four x
+// coordinates of a row are x, x*t, x*t^2, x*t^3 with t a primitive 4th root of unity, the row polynomial evaluated at
+// alpha is a 4-point inverse DFT followed by Horner in u = alpha / x:
+//      f(alpha) = 1/4 * sum_j u^j * sum_k y_k t^(-jk)
+// and 1/x is a power of the inverse LDE root (table lookup): no field inversion is needed.  The interpolating cubic is
+// unique and the arithmetic exact, hence the values equal the reference's.
+#include "poly.h"
+#include "blake3.cuh"
+
+namespace dg {
+
+__global__ void __launch_bounds__(256) fri_hash_rows_kernel(const fe *__restrict__ v, Layout in, Layout rows, uint4 *__restrict__ leaves) {
+    const unsigned long long R = 1ULL << rows.log_d;
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R) return;
+    const unsigned long long r = rows.logical(t);
+    uint32_t m[16], cv[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint4 x = reinterpret_cast<const uint4 *>(v)[in.phys(r + (unsigned long long)j * R)];
+        m[4 * j] = x.x; m[4 * j + 1] = x.y; m[4 * j + 2] = x.z; m[4 * j + 3] = x.w;
+    }
+    b3::hash64(m, cv);
+    leaves[2 * r] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    leaves[2 * r + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+void fri_hash_rows(Context &c, const fe *values, Layout in, Layout rows, void *leaves) {
+    const unsigned long long R = 1ULL << rows.log_d;
+    fri_hash_rows_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c.stream>>>(values, in, rows, (uint4 *)leaves);
+    DG_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) fri_fold_kernel(const fe *__restrict__ v, Layout in, fe *__restrict__ next, Layout out, fe alpha,
+                                                       TwiddleRef inv_root, int shift, fe tau_inv, fe inv4) {
+    const unsigned long long R = 1ULL << out.log_d;
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R) return;
+    const unsigned long long r = out.logical(t);
+    fe y0 = v[in.phys(r)], y1 = v[in.phys(r + R)], y2 = v[in.phys(r + 2 * R)], y3 = v[in.phys(r + 3 * R)];
+    // x_r^-1 = (w_N^-1)^(r << shift)
+    const unsigned ee = (unsigned)((r << shift) & (unsigned long long)inv_root.mask);
+    fe xinv = fe_mul(inv_root.lo[ee & ((1u << inv_root.lo_bits) - 1u)], inv_root.hi[ee >> inv_root.lo_bits]);
+    fe u = fe_mul(alpha, xinv);
+    fe s02 = fe_add(y0, y2), d02 = fe_sub(y0, y2), s13 = fe_add(y1, y3), d13 = fe_mul(fe_sub(y1, y3), tau_inv);
+    fe a0 = fe_add(s02, s13), a1 = fe_add(d02, d13), a2 = fe_sub(s02, s13), a3 = fe_sub(d02, d13);
+    fe acc = fe_add(a2, fe_mul(u, a3));
+    acc = fe_add(a1, fe_mul(u, acc));
+    acc = fe_add(a0, fe_mul(u, acc));
+    next[t] = fe_mul(acc, inv4);
+}
+void fri_fold(Context &c, const fe *values, Layout in, fe *next, Layout out, fe alpha, const TwiddleRef &inv_root_table, int log_n_total,
+              fe tau_inv, fe inv4) {
+    const unsigned long long R = 1ULL << out.log_d;
+    const int shift = log_n_total - in.log_d;            // layer domain is the 4^depth-th powers of the LDE domain
+    fri_fold_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c.stream>>>(values, in, next, out, alpha, inv_root_table, shift, tau_inv, inv4);
+    DG_CUDA(cudaGetLastError());
+}
+
+// nodes[L/2 + j] = H(ev[4j], ev[4j+1], ev[4j+2], ev[4j+3]) with L = N/2 two-element leaves (prover.rs:84-86, 180-187)
+__global__ void __launch_bounds__(256) constraint_first_level_kernel(const fe *__restrict__ ev, int log_n, int log_blowup, uint4 *__restrict__ nodes) {
+    const unsigned long long n = 1ULL << log_n;
+    const unsigned long long quarter = (n << log_blowup) >> 2;
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= quarter) return;
+    const unsigned long long c4 = t >> log_n, k = t & (n - 1);
+    const unsigned long long j = (k << (log_blowup - 2)) + c4;
+    uint32_t m[16], cv[8];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const uint4 x = reinterpret_cast<const uint4 *>(ev)[(4 * c4 + u) * n + k];
+        m[4 * u] = x.x; m[4 * u + 1] = x.y; m[4 * u + 2] = x.z; m[4 * u + 3] = x.w;
+    }
+    b3::hash64(m, cv);
+    nodes[2 * (quarter + j)] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    nodes[2 * (quarter + j) + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+void constraint_tree_first_level(Context &c, const fe *evals, int log_n, int log_blowup, void *nodes) {
+    const unsigned long long quarter = (1ULL << (log_n + log_blowup)) >> 2;
+    constraint_first_level_kernel<<<(unsigned)((quarter + 255) / 256), 256, 0, c.stream>>>(evals, log_n, log_blowup, (uint4 *)nodes);
+    DG_CUDA(cudaGetLastError());
+}
+
+}  // namespace dg

@@ -140,6 +140,22 @@ void merkle_build(Context &c, const void *leaves, void *nodes, unsigned long lon
     }
 }
 
+// completes a tree whose level with m nodes (m a power of two) already sits at nodes[m .. 2m)
+void merkle_finish(Context &c, void *nodes, unsigned long long m) {
+    uint4 *nd = (uint4 *)nodes;
+    while (m > 1024) {
+        merkle_level_kernel<<<(unsigned)((m / 2 + 255) / 256), 256, 0, c.stream>>>(nd + 2 * m, nd + m, m / 2);
+        DG_CUDA(cudaGetLastError());
+        m >>= 1;
+    }
+    if (m >= 2) {
+        merkle_top_kernel<<<1, 512, 0, c.stream>>>(nd, (unsigned)m);
+        DG_CUDA(cudaGetLastError());
+    } else {
+        DG_CUDA(cudaMemsetAsync(nd, 0, 32, c.stream));
+    }
+}
+
 // ---- generic 64-byte hashing (tests / FRI rows given contiguously) ------------------------------------------------------
 void hash64_contiguous(Context &c, const void *in, void *out, unsigned long long count) {
     merkle_level_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c.stream>>>((const uint4 *)in, (uint4 *)out, count);
