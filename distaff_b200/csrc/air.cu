@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(128) constraint_eval_kernel(const AirParams P)
 void launch_constraint_eval(Context &c, const AirParams &P) {
     air_upload_constants();
     const unsigned long long E = 8ULL << P.log_n;
-    constraint_eval_kernel<<<(unsigned)((E + 127) / 128), 128, 0, c.stream>>>(P);
+    constraint_eval_kernel<<<(unsigned)((E + 127) / 128), 128, 0, c.stream>>>(P); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 

@@ -118,7 +118,7 @@ int dg_dev_flush_l2(void) {
         static DevBuf scratch;
         const size_t bytes = (size_t)256 << 20;
         scratch.ensure(bytes);
-        fill_kernel<<<(unsigned)(bytes / 16 / 256), 256, 0, c.stream>>>(scratch.as<uint4>(), bytes / 16, 7u);
+        fill_kernel<<<(unsigned)(bytes / 16 / 256), 256, 0, c.stream>>>(scratch.as<uint4>(), bytes / 16, 7u); c.launches++;
         DG_CUDA(cudaGetLastError());
         DG_CUDA(cudaStreamSynchronize(c.stream));
     });
@@ -197,7 +197,7 @@ int dg_lde(const uint8_t *values, uint8_t *extended, uint32_t log_n, uint32_t lo
         DG_CUDA(cudaMemcpyAsync(d_in.p, values, n * batch * 16, cudaMemcpyHostToDevice, c.stream));
         ntt_batch(c, d_in.as<fe>(), d_in.as<fe>(), log_n, batch, n, n, true);                 // interpolate (trace_table.rs:158)
         lde_batch(c, d_in.as<fe>(), d_ext.as<fe>(), log_n, log_blowup, 1, batch, n, N);       // evaluate over the LDE domain (:165)
-        coset_to_logical_kernel<<<dim3((unsigned)((N + 255) / 256), batch), 256, 0, c.stream>>>(d_ext.as<fe>(), d_out.as<fe>(), log_n, log_blowup);
+        coset_to_logical_kernel<<<dim3((unsigned)((N + 255) / 256), batch), 256, 0, c.stream>>>(d_ext.as<fe>(), d_out.as<fe>(), log_n, log_blowup); c.launches++;
         DG_CUDA(cudaGetLastError());
         DG_CUDA(cudaMemcpyAsync(extended, d_out.p, N * batch * 16, cudaMemcpyDeviceToHost, c.stream));
         DG_CUDA(cudaStreamSynchronize(c.stream));
@@ -245,7 +245,7 @@ int dg_field_op(int op, int impl, const uint8_t *a, const uint8_t *b, uint8_t *o
         DevBuf da(n * 16), db(n * 16), dout(n * 16);
         DG_CUDA(cudaMemcpyAsync(da.p, a, n * 16, cudaMemcpyHostToDevice, c.stream));
         if (b) DG_CUDA(cudaMemcpyAsync(db.p, b, n * 16, cudaMemcpyHostToDevice, c.stream));
-        field_op_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(op, impl, da.as<fe>(), b ? db.as<fe>() : nullptr, dout.as<fe>(), n);
+        field_op_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(op, impl, da.as<fe>(), b ? db.as<fe>() : nullptr, dout.as<fe>(), n); c.launches++;
         DG_CUDA(cudaGetLastError());
         DG_CUDA(cudaMemcpyAsync(out, dout.p, n * 16, cudaMemcpyDeviceToHost, c.stream));
         DG_CUDA(cudaStreamSynchronize(c.stream));

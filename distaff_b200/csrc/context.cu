@@ -88,8 +88,8 @@ TwiddleRef Context::twiddle(int log_order, bool inverse) {
         fe whi = host_pow(w, lo_n);
         t.lo.alloc(lo_n * sizeof(fe));
         t.hi.alloc(hi_n * sizeof(fe));
-        power_table_kernel<<<(lo_n + 127) / 128, 128, 0, stream>>>(t.lo.as<fe>(), w, lo_n);
-        power_table_kernel<<<(hi_n + 127) / 128, 128, 0, stream>>>(t.hi.as<fe>(), whi, hi_n);
+        power_table_kernel<<<(lo_n + 127) / 128, 128, 0, stream>>>(t.lo.as<fe>(), w, lo_n); launches++;
+        power_table_kernel<<<(hi_n + 127) / 128, 128, 0, stream>>>(t.hi.as<fe>(), whi, hi_n); launches++;
         DG_CUDA(cudaGetLastError());
         it = twiddles.emplace(key, std::move(t)).first;
     }

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) fri_hash_rows_kernel(const fe *__restrict
 }
 void fri_hash_rows(Context &c, const fe *values, Layout in, Layout rows, void *leaves) {
     const unsigned long long R = 1ULL << rows.log_d;
-    fri_hash_rows_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c.stream>>>(values, in, rows, (uint4 *)leaves);
+    fri_hash_rows_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c.stream>>>(values, in, rows, (uint4 *)leaves); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
@@ -59,7 +59,7 @@ void fri_fold(Context &c, const fe *values, Layout in, fe *next, Layout out, fe 
               fe tau_inv, fe inv4) {
     const unsigned long long R = 1ULL << out.log_d;
     const int shift = log_n_total - in.log_d;            // layer domain is the 4^depth-th powers of the LDE domain
-    fri_fold_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c.stream>>>(values, in, next, out, alpha, inv_root_table, shift, tau_inv, inv4);
+    fri_fold_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c.stream>>>(values, in, next, out, alpha, inv_root_table, shift, tau_inv, inv4); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) constraint_first_level_kernel(const fe *_
 }
 void constraint_tree_first_level(Context &c, const fe *evals, int log_n, int log_blowup, void *nodes) {
     const unsigned long long quarter = (1ULL << (log_n + log_blowup)) >> 2;
-    constraint_first_level_kernel<<<(unsigned)((quarter + 255) / 256), 256, 0, c.stream>>>(evals, log_n, log_blowup, (uint4 *)nodes);
+    constraint_first_level_kernel<<<(unsigned)((quarter + 255) / 256), 256, 0, c.stream>>>(evals, log_n, log_blowup, (uint4 *)nodes); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 

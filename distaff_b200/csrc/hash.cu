@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) hash_rows_kernel(const fe *__restrict__ e
 
 void hash_trace_rows(Context &c, const fe *ext, void *leaves, int w, int log_n, int log_blowup) {
     const unsigned long long N = 1ULL << (log_n + log_blowup);
-    hash_rows_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(ext, (uint4 *)leaves, w, N, log_n, log_blowup);
+    hash_rows_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(ext, (uint4 *)leaves, w, N, log_n, log_blowup); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
@@ -126,14 +126,14 @@ void merkle_build(Context &c, const void *leaves, void *nodes, unsigned long lon
     unsigned long long m = L / 2;
     // first level reads the leaves; afterwards each level reads the one below it inside `nodes`
     while (true) {
-        merkle_level_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(in, nd + 2 * m, m);
+        merkle_level_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(in, nd + 2 * m, m); c.launches++;
         DG_CUDA(cudaGetLastError());
         if (m <= 1024) break;
         in = nd + 2 * m;
         m >>= 1;
     }
     if (m >= 2) {
-        merkle_top_kernel<<<1, 512, 0, c.stream>>>(nd, (unsigned)m);
+        merkle_top_kernel<<<1, 512, 0, c.stream>>>(nd, (unsigned)m); c.launches++;
         DG_CUDA(cudaGetLastError());
     } else {
         DG_CUDA(cudaMemsetAsync(nd, 0, 32, c.stream));   // L == 2: nodes[1] already written, nodes[0] = 0
@@ -144,12 +144,12 @@ void merkle_build(Context &c, const void *leaves, void *nodes, unsigned long lon
 void merkle_finish(Context &c, void *nodes, unsigned long long m) {
     uint4 *nd = (uint4 *)nodes;
     while (m > 1024) {
-        merkle_level_kernel<<<(unsigned)((m / 2 + 255) / 256), 256, 0, c.stream>>>(nd + 2 * m, nd + m, m / 2);
+        merkle_level_kernel<<<(unsigned)((m / 2 + 255) / 256), 256, 0, c.stream>>>(nd + 2 * m, nd + m, m / 2); c.launches++;
         DG_CUDA(cudaGetLastError());
         m >>= 1;
     }
     if (m >= 2) {
-        merkle_top_kernel<<<1, 512, 0, c.stream>>>(nd, (unsigned)m);
+        merkle_top_kernel<<<1, 512, 0, c.stream>>>(nd, (unsigned)m); c.launches++;
         DG_CUDA(cudaGetLastError());
     } else {
         DG_CUDA(cudaMemsetAsync(nd, 0, 32, c.stream));
@@ -158,7 +158,7 @@ void merkle_finish(Context &c, void *nodes, unsigned long long m) {
 
 // ---- generic 64-byte hashing (tests / FRI rows given contiguously) ------------------------------------------------------
 void hash64_contiguous(Context &c, const void *in, void *out, unsigned long long count) {
-    merkle_level_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c.stream>>>((const uint4 *)in, (uint4 *)out, count);
+    merkle_level_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c.stream>>>((const uint4 *)in, (uint4 *)out, count); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
@@ -189,7 +189,7 @@ unsigned long long pow_search(Context &c, const uint8_t seed[32], unsigned grind
     unsigned long long start = 1;
     const unsigned long long batch = 1ULL << 22;
     for (int iter = 0; iter < (1 << 20); iter++) {
-        pow_kernel<<<(unsigned)(batch / 256), 256, 0, c.stream>>>(d_seed.as<uint32_t>(), start, batch, grinding, d_best.as<unsigned long long>());
+        pow_kernel<<<(unsigned)(batch / 256), 256, 0, c.stream>>>(d_seed.as<uint32_t>(), start, batch, grinding, d_best.as<unsigned long long>()); c.launches++;
         DG_CUDA(cudaGetLastError());
         unsigned long long best;
         DG_CUDA(cudaMemcpyAsync(&best, d_best.p, 8, cudaMemcpyDeviceToHost, c.stream));
@@ -205,7 +205,7 @@ unsigned long long pow_search(Context &c, const uint8_t seed[32], unsigned grind
 namespace dg {
 // rows of a plain column-major matrix (no coset permutation): physical position == logical row
 void hash_rows_plain(Context &c, const fe *cols, void *digests, int w, unsigned long long rows) {
-    hash_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c.stream>>>(cols, (uint4 *)digests, w, rows, 63, 0);
+    hash_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c.stream>>>(cols, (uint4 *)digests, w, rows, 63, 0); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 // host-side BLAKE3 of the 64-byte proof-of-work input seed || nonce_le || 0^24 (proof_of_work.rs:12-24)

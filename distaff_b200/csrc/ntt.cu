@@ -140,7 +140,7 @@ static void launch_pass(Context &c, int log_l, PassGeom g, const fe *src, fe *ds
         attr_set[log_l] = true;
     }
     DG_REQUIRE(by <= 65535 && bz <= 65535, "batch too large for one launch");
-    k<<<dim3(blocks_x, by, bz), threads, smem, c.stream>>>(src, dst, g);
+    k<<<dim3(blocks_x, by, bz), threads, smem, c.stream>>>(src, dst, g); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 

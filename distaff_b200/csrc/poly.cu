@@ -30,8 +30,8 @@ PowTable::PowTable(Context &c, fe base, unsigned long long len) {
     lo.alloc(lo_n * sizeof(fe));
     hi.alloc(hi_n * sizeof(fe));
     fe step = fe_pow_u64(base, lo_n);
-    pow_fill_kernel<<<(unsigned)((lo_n + 127) / 128), 128, 0, c.stream>>>(lo.as<fe>(), base, lo_n);
-    pow_fill_kernel<<<(unsigned)((hi_n + 127) / 128), 128, 0, c.stream>>>(hi.as<fe>(), step, hi_n);
+    pow_fill_kernel<<<(unsigned)((lo_n + 127) / 128), 128, 0, c.stream>>>(lo.as<fe>(), base, lo_n); c.launches++;
+    pow_fill_kernel<<<(unsigned)((hi_n + 127) / 128), 128, 0, c.stream>>>(hi.as<fe>(), step, hi_n); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
@@ -102,15 +102,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(fe *__restrict
 void suffix_scan_exclusive(Context &c, fe *data, unsigned long long len) {
     const unsigned long long nblk = (len + SCAN_BLOCK - 1) / SCAN_BLOCK;
     if (nblk == 1) {
-        scan_apply_kernel<<<1, SCAN_THREADS, 0, c.stream>>>(data, nullptr, len);
+        scan_apply_kernel<<<1, SCAN_THREADS, 0, c.stream>>>(data, nullptr, len); c.launches++;
         DG_CUDA(cudaGetLastError());
         return;
     }
     DevBuf sums(nblk * sizeof(fe));
-    scan_block_sums_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, c.stream>>>(data, sums.as<fe>(), len);
+    scan_block_sums_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, c.stream>>>(data, sums.as<fe>(), len); c.launches++;
     DG_CUDA(cudaGetLastError());
     suffix_scan_exclusive(c, sums.as<fe>(), nblk);
-    scan_apply_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, c.stream>>>(data, sums.as<fe>(), len);
+    scan_apply_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, c.stream>>>(data, sums.as<fe>(), len); c.launches++;
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaStreamSynchronize(c.stream));            // `sums` is released on return
 }
@@ -128,10 +128,10 @@ __global__ void scale_by_pow_kernel(const fe *__restrict__ in, fe *__restrict__ 
 // out[i] = sum_{j>i} (in[j] - [j==0] sub0) b^(j-i-1);   `scratch` holds len elements.  in may equal out.
 void syn_div(Context &c, const fe *in, fe *out, fe *scratch, unsigned long long len, const PowRef &b_pows, const PowRef &binv_pows, fe sub0) {
     const unsigned blocks = (unsigned)((len + 255) / 256);
-    scale_by_pow_kernel<<<blocks, 256, 0, c.stream>>>(in, scratch, b_pows, 0, len, sub0);
+    scale_by_pow_kernel<<<blocks, 256, 0, c.stream>>>(in, scratch, b_pows, 0, len, sub0); c.launches++;
     DG_CUDA(cudaGetLastError());
     suffix_scan_exclusive(c, scratch, len);
-    scale_by_pow_kernel<<<blocks, 256, 0, c.stream>>>(scratch, out, binv_pows, 1, len, fe_make(0, 0));
+    scale_by_pow_kernel<<<blocks, 256, 0, c.stream>>>(scratch, out, binv_pows, 1, len, fe_make(0, 0)); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
@@ -161,8 +161,8 @@ __global__ void expanded_stencil_kernel(const fe *__restrict__ s, const fe *__re
     out[idx] = v;
 }
 void syn_div_expanded_sum(Context &c, const fe *a, fe *scratch, const fe *add0, const fe *add1, fe *out, unsigned long long n, unsigned long long len, fe e) {
-    strided_suffix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(a, scratch, n, (int)(len / n));
-    expanded_stencil_kernel<<<(unsigned)((len + 255) / 256), 256, 0, c.stream>>>(scratch, add0, add1, out, n, len, e);
+    strided_suffix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(a, scratch, n, (int)(len / n)); c.launches++;
+    expanded_stencil_kernel<<<(unsigned)((len + 255) / 256), 256, 0, c.stream>>>(scratch, add0, add1, out, n, len, e); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
@@ -214,8 +214,8 @@ __global__ void reduce_partials_kernel(const fe *__restrict__ partial, fe *__res
 void eval_polys_at(Context &c, const fe *polys, unsigned long long n, int cols, const PowRef &zt, const TwiddleRef &gt, bool two_points, fe *out) {
     const unsigned chunks = (unsigned)((n + EVAL_CHUNK - 1) / EVAL_CHUNK);
     DevBuf partial((size_t)cols * 2 * chunks * sizeof(fe));
-    eval2_partial_kernel<<<dim3(chunks, cols), 256, 0, c.stream>>>(polys, n, zt, gt, partial.as<fe>(), two_points ? 1 : 0);
-    reduce_partials_kernel<<<cols * 2, 32, 0, c.stream>>>(partial.as<fe>(), out, chunks);
+    eval2_partial_kernel<<<dim3(chunks, cols), 256, 0, c.stream>>>(polys, n, zt, gt, partial.as<fe>(), two_points ? 1 : 0); c.launches++;
+    reduce_partials_kernel<<<cols * 2, 32, 0, c.stream>>>(partial.as<fe>(), out, chunks); c.launches++;
     DG_CUDA(cudaGetLastError());
     DG_CUDA(cudaStreamSynchronize(c.stream));
 }
@@ -235,7 +235,7 @@ __global__ void lincomb2_kernel(const fe *__restrict__ polys, unsigned long long
     t1[k] = a; t2[k] = b;
 }
 void lincomb2(Context &c, const fe *polys, unsigned long long n, int w, const fe *cc1, const fe *cc2, fe *t1, fe *t2) {
-    lincomb2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(polys, n, w, cc1, cc2, t1, t2);
+    lincomb2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(polys, n, w, cc1, cc2, t1, t2); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
@@ -252,7 +252,7 @@ __global__ void compose_kernel(const fe *__restrict__ t1q, const fe *__restrict_
 }
 void compose(Context &c, const fe *t1q, const fe *t2q, const fe *cq, fe *comp, unsigned long long n, unsigned long long len, unsigned long long inc,
              fe k1, fe k2, fe kc) {
-    compose_kernel<<<(unsigned)((len + 255) / 256), 256, 0, c.stream>>>(t1q, t2q, cq, comp, n, len, inc, k1, k2, kc);
+    compose_kernel<<<(unsigned)((len + 255) / 256), 256, 0, c.stream>>>(t1q, t2q, cq, comp, n, len, inc, k1, k2, kc); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
@@ -269,7 +269,7 @@ __global__ void gather_rows_kernel(const fe *__restrict__ ext, int w, int log_n,
     out[t] = ext[(unsigned long long)j * N + (c << log_n) + k];
 }
 void gather_rows(Context &c, const fe *ext, int w, int log_n, int log_blowup, const unsigned long long *d_positions, int nq, fe *d_out) {
-    gather_rows_kernel<<<(nq * w + 127) / 128, 128, 0, c.stream>>>(ext, w, log_n, log_blowup, d_positions, nq, d_out);
+    gather_rows_kernel<<<(nq * w + 127) / 128, 128, 0, c.stream>>>(ext, w, log_n, log_blowup, d_positions, nq, d_out); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 // out[t] = src[idx[t]] for 32-byte items
@@ -281,7 +281,7 @@ __global__ void gather32_kernel(const uint4 *__restrict__ src, const unsigned lo
 }
 void gather32(Context &c, const void *src, const unsigned long long *d_idx, int count, void *d_out) {
     if (count == 0) return;
-    gather32_kernel<<<(count + 127) / 128, 128, 0, c.stream>>>((const uint4 *)src, d_idx, count, (uint4 *)d_out);
+    gather32_kernel<<<(count + 127) / 128, 128, 0, c.stream>>>((const uint4 *)src, d_idx, count, (uint4 *)d_out); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 // out[t] = src[idx[t]] for 16-byte items
@@ -291,7 +291,7 @@ __global__ void gather16_kernel(const fe *__restrict__ src, const unsigned long 
 }
 void gather16(Context &c, const fe *src, const unsigned long long *d_idx, int count, fe *d_out) {
     if (count == 0) return;
-    gather16_kernel<<<(count + 127) / 128, 128, 0, c.stream>>>(src, d_idx, count, d_out);
+    gather16_kernel<<<(count + 127) / 128, 128, 0, c.stream>>>(src, d_idx, count, d_out); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
