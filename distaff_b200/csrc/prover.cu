@@ -43,6 +43,16 @@ void debug_dump(Context &c, const char *name, const void *dev, size_t bytes) {
     fclose(f);
 }
 
+void debug_dump_host(const char *name, const void *host, size_t bytes) {
+    const char *dir = getenv("DG_DEBUG_DUMP");
+    if (!dir) return;
+    std::string path = std::string(dir) + "/" + name + ".bin";
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return;
+    fwrite(host, 1, bytes, f);
+    fclose(f);
+}
+
 typedef std::array<uint8_t, 32> Digest;
 
 // fetches 32-byte items src[idx[i]] to the host
@@ -298,12 +308,14 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
         std::vector<uint8_t> roots;
         for (auto &L : layers) roots.insert(roots.end(), L.root.begin(), L.root.end());
         uint8_t seed[32];
+        debug_dump_host("fri_roots", roots.data(), roots.size());
         fs::blake3_short(roots.data(), roots.size(), seed);
         proof->pow_nonce = pow_search(c, seed, opt.grinding_factor);
         pow_hash(seed, proof->pow_nonce, proof->pow_seed);
         try {
             positions = fs::query_positions(proof->pow_seed, N, b, opt.num_queries);
         } catch (const std::exception &e) { throw Error(DG_ERR_EXHAUSTED, e.what()); }
+        debug_dump_host("positions", positions.data(), positions.size() * 8);
     }
 
     // ---- 9: build proof object -------------------------------------------------------------------------------------------------------------------------

@@ -20,6 +20,16 @@ def dg():
     return distaff_b200
 
 
+def _same(proof, ref):
+    """byte equality with a readable diagnosis (which commitment diverged first)"""
+    if proof.bytes == ref.proof:
+        return
+    diff = [i for i in range(min(len(proof.bytes), len(ref.proof))) if proof.bytes[i] != ref.proof[i]]
+    raise AssertionError("proof mismatch: len %d vs %d, trace_root %s, constraint_root %s, nonce %s vs %s, %d differing bytes from offset %s" % (
+        len(proof.bytes), len(ref.proof), proof.trace_root == ref.digest("trace_root"), proof.constraint_root == ref.digest("constraint_root"),
+        proof.pow_nonce, ref.u64s("pow_nonce")[0], len(diff), diff[:5]))
+
+
 @pytest.fixture(scope="module")
 def small():
     return programs.small_programs()
@@ -40,14 +50,22 @@ def test_proofs_are_bit_identical_to_the_oracle(dg, po, small):
         assert proof.stats["kernel_launches"] > 0
 
 
-@pytest.mark.parametrize("ext,queries,grinding", [(16, 30, 8), (64, 20, 12), (128, 10, 0), (256, 5, 4)])
-def test_other_proof_options(dg, po, small, ext, queries, grinding):
-    tr = small["collatz3"]
+@pytest.mark.parametrize("prog,ext,queries,grinding", [("collatz3", 16, 30, 8), ("collatz3", 64, 20, 12), ("collatz3", 128, 10, 0),
+                                                        ("fib13", 256, 5, 4), ("collatz3", 256, 5, 4), ("hash", 128, 128, 1)])
+def test_other_proof_options(dg, po, small, prog, ext, queries, grinding):
+    tr = small[prog]
     proof = dg.prove(tr, dg.ProofOptions(ext, queries, grinding))
     ref = po.prove(tr.registers, tr.ctx_depth, tr.loop_depth, tr.public_inputs, tr.outputs, ext=ext, num_queries=queries, grinding=grinding)
     assert ref.error is None
-    assert proof.bytes == ref.proof
-    assert po.verify(tr.program_hash, tr.public_inputs, tr.outputs, proof.bytes) is None
+    _same(proof, ref)
+    verdict = po.verify(tr.program_hash, tr.public_inputs, tr.outputs, proof.bytes)
+    if prog == "collatz3" and ext == 256:
+        # reference quirk, reproduced by the restated verifier: fri/verifier.rs:86 divides max_degree_plus_1 by 4 per layer with
+        # truncation, so for blowup 256 and odd log2(trace length) (here 2^11) it demands a remainder of degree 2 where the
+        # honest remainder has degree 3.  The prover output is still byte-identical to the reference prover's.
+        assert verdict == "verification of low-degree proof failed: remainder is not a valid degree 2 polynomial"
+    else:
+        assert verdict is None
 
 
 def test_medium_traces(dg, po):

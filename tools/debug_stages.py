@@ -16,13 +16,14 @@ from oracle import pyoracle as po      # noqa: E402
 from tests import programs             # noqa: E402
 
 names = sys.argv[1:] or ["fib13"]
+EXT, NQ, GR = [int(x) for x in os.environ.get("DG_OPTS", "32,50,20").split(",")]
 P = programs.small_programs()
 for name in names:
     tr = P[name]
-    ref = po.prove(tr.registers, tr.ctx_depth, tr.loop_depth, tr.public_inputs, tr.outputs, keep_large=True)
+    ref = po.prove(tr.registers, tr.ctx_depth, tr.loop_depth, tr.public_inputs, tr.outputs, ext=EXT, num_queries=NQ, grinding=GR, keep_large=True)
     print(name, "oracle error:", ref.error, "n=", tr.length, "w=", tr.width)
     try:
-        proof = dg.prove(tr)
+        proof = dg.prove(tr, dg.ProofOptions(EXT, NQ, GR))
     except Exception as e:
         print("  GPU prove failed:", e)
         proof = None
@@ -36,7 +37,18 @@ for name in names:
         same = got.shape == want.shape and np.array_equal(got, want)
         bad = None if same else (np.nonzero((got != want).any(axis=1))[0][:8] if got.shape == want.shape else "shape %s vs %s" % (got.shape, want.shape))
         print("  ", vec, "OK" if same else f"MISMATCH at {bad}")
+    fr = os.path.join(d, "fri_roots.bin")
+    if os.path.exists(fr):
+        got = open(fr, "rb").read()
+        want = b"".join(ref.digests("fri_roots"))
+        print("   fri_roots", [got[i:i + 32] == want[i:i + 32] for i in range(0, max(len(got), len(want)), 32)])
+    ps = os.path.join(d, "positions.bin")
+    if os.path.exists(ps):
+        print("   positions", list(np.fromfile(ps, dtype=np.uint64)) == ref.u64s("positions"))
     if proof:
         print("   trace_root", proof.trace_root == ref.digest("trace_root"), "constraint_root", proof.constraint_root == ref.digest("constraint_root"),
               "nonce", proof.pow_nonce == ref.u64s("pow_nonce")[0], "bytes", proof.bytes == ref.proof, len(proof.bytes), len(ref.proof))
+        if proof.bytes != ref.proof and len(proof.bytes) == len(ref.proof):
+            diff = [i for i in range(len(ref.proof)) if proof.bytes[i] != ref.proof[i]]
+            print("   first differing byte offsets:", diff[:10], "count", len(diff))
         print("   stats", proof.stats)
