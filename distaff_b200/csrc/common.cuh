@@ -30,7 +30,11 @@ struct Error : public std::runtime_error {
         if (!(cond)) throw dg::Error(-1, std::string(msg));        \
     } while (0)
 
-// simple RAII device buffer
+// stream on which DevBuf allocations are ordered (the context's stream once it exists)
+cudaStream_t &alloc_stream();
+
+// RAII device buffer backed by the stream-ordered allocator (cudaMallocAsync): after the first proof the pool serves every
+// request without touching the driver, so per-proof buffers (tens of GB at 2^20 steps) cost microseconds to obtain
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
@@ -44,11 +48,11 @@ struct DevBuf {
     void alloc(size_t n) {
         release();
         if (n == 0) return;
-        DG_CUDA(cudaMalloc(&p, n));
+        DG_CUDA(cudaMallocAsync(&p, n, alloc_stream()));
         bytes = n;
     }
     void ensure(size_t n) { if (bytes < n) alloc(n); }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() { if (p) cudaFreeAsync(p, alloc_stream()); p = nullptr; bytes = 0; }
     template <typename T> T *as() const { return (T *)p; }
 };
 

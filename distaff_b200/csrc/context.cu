@@ -22,6 +22,9 @@ __global__ void power_table_kernel(fe *out, fe step, unsigned count) {
     if (i < count) out[i] = fe_pow_u64(step, i);
 }
 
+static cudaStream_t g_alloc_stream = nullptr;
+cudaStream_t &alloc_stream() { return g_alloc_stream; }
+
 static std::once_flag g_once;
 static Context *g_ctx = nullptr;
 static int g_device = -1;
@@ -39,6 +42,13 @@ static void build_context(int device) {
     DG_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     DG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    g_alloc_stream = c->stream;
+    {   // keep freed blocks in the pool instead of returning them to the driver between proofs
+        cudaMemPool_t pool;
+        DG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long threshold = ~0ULL;
+        DG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    }
     // small root tables
     size_t total = 0;
     for (int l = 1; l <= MAX_LOG_L; l++) { c->small_root_offset[l] = total; total += (size_t)1 << (l - 1); }

@@ -112,7 +112,6 @@ void suffix_scan_exclusive(Context &c, fe *data, unsigned long long len) {
     suffix_scan_exclusive(c, sums.as<fe>(), nblk);
     scan_apply_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, c.stream>>>(data, sums.as<fe>(), len); c.launches++;
     DG_CUDA(cudaGetLastError());
-    DG_CUDA(cudaStreamSynchronize(c.stream));            // `sums` is released on return
 }
 
 // ---- synthetic division by (x - b) ----------------------------------------------------------------------------------------------------
@@ -217,7 +216,6 @@ void eval_polys_at(Context &c, const fe *polys, unsigned long long n, int cols, 
     eval2_partial_kernel<<<dim3(chunks, cols), 256, 0, c.stream>>>(polys, n, zt, gt, partial.as<fe>(), two_points ? 1 : 0); c.launches++;
     reduce_partials_kernel<<<cols * 2, 32, 0, c.stream>>>(partial.as<fe>(), out, chunks); c.launches++;
     DG_CUDA(cudaGetLastError());
-    DG_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 // ---- linear combinations ------------------------------------------------------------------------------------------------------------------

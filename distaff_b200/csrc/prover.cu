@@ -224,7 +224,6 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
         syn_div(c, ic, ic, scratch.as<fe>(), E, one_t.ref(), one_t.ref(), fe_make(0, 0));            // / (x - 1)
         syn_div(c, fc, fc, scratch.as<fe>(), E, xl_t.ref(), xli_t.ref(), fe_make(0, 0));             // / (x - x_last)
         syn_div_expanded_sum(c, tc, scratch.as<fe>(), ic, fc, combined.as<fe>(), n, E, x_last);      // / ((x^n - 1)/(x - x_last)), summed
-        DG_CUDA(cudaStreamSynchronize(c.stream));
     }
     debug_dump(c, "constraint_poly", combined.p, E * 16);
 
@@ -268,7 +267,6 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
         compose(c, t1, t2, scratch2.as<fe>(), comp.as<fe>(), n, E, 6 * n + 1, dc.t1_degree, dc.t2_degree, dc.constraints);
         debug_dump(c, "composition_poly", comp.p, E * 16);
         lde_batch(c, comp.as<fe>(), comp_ext.as<fe>(), log_n, log_b, 8, 1, E, N);
-        DG_CUDA(cudaStreamSynchronize(c.stream));
     }
 
     // ---- 7: FRI layers ---------------------------------------------------------------------------------------------------------------------------
