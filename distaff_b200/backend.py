@@ -60,6 +60,11 @@ EXPORTS = {
     "dg_dev_merkle_build": [vp, u64, vp, fp],
     "dg_dev_hash_rows": [vp, u32, u32, u32, vp, fp],
     "dg_dev_flush_l2": [],
+    "dg_host_prng_vector": [vp, u64, vp],
+    "dg_host_query_positions": [vp, u64, u32, u32, vp],
+    "dg_host_blake3": [vp, ctypes.c_size_t, vp],
+    "dg_host_plan_batch": [vp, u32, u64, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],
+    "dg_host_periodic_tables": [vp],
 }
 VOID_EXPORTS = {"dg_proof_free": [vp]}
 

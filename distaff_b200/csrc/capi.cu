@@ -2,6 +2,7 @@
 #include "../../include/distaff_gpu.h"
 #include "common.cuh"
 #include "prover.h"
+#include "host_fs.h"
 
 namespace dg {
 void hash_trace_rows(Context &c, const fe *ext, void *leaves, int w, int log_n, int log_blowup);
@@ -295,5 +296,35 @@ int dg_proof_pow_nonce(const dg_proof_t *proof, uint64_t *nonce) {
     return guarded([&] { DG_REQUIRE(proof && nonce, "null argument"); *nonce = ((const Proof *)proof)->pow_nonce; });
 }
 void dg_proof_free(dg_proof_t *proof) { delete (Proof *)proof; }
+
+// ---- host-only helpers (no device access) ---------------------------------------------------------------------------------------------
+int dg_host_prng_vector(const uint8_t seed[32], uint64_t count, uint8_t *out16) {
+    return guarded([&] { std::vector<fe> v = fs::prng_vector(seed, count); memcpy(out16, v.data(), count * 16); });
+}
+int dg_host_query_positions(const uint8_t seed[32], uint64_t domain_size, uint32_t extension_factor, uint32_t num_queries, uint64_t *out) {
+    return guarded([&] {
+        try {
+            std::vector<uint64_t> p = fs::query_positions(seed, domain_size, extension_factor, num_queries);
+            memcpy(out, p.data(), p.size() * 8);
+        } catch (const std::exception &e) { throw Error(DG_ERR_EXHAUSTED, e.what()); }
+    });
+}
+int dg_host_blake3(const uint8_t *data, size_t len, uint8_t out32[32]) { return guarded([&] { fs::blake3_short(data, len, out32); }); }
+int dg_host_plan_batch(const uint64_t *indexes, uint32_t n_indexes, uint64_t n_leaves, uint64_t *out, size_t cap, size_t *written) {
+    return guarded([&] {
+        fs::BatchPlan plan = fs::plan_batch_proof(std::vector<uint64_t>(indexes, indexes + n_indexes), n_leaves);
+        std::vector<uint64_t> flat = {(uint64_t)plan.nodes.size(), (uint64_t)plan.depth};
+        for (auto &slot : plan.nodes) {
+            flat.push_back(slot.size());
+            for (auto &r : slot) { flat.push_back(r.leaf ? 1 : 0); flat.push_back(r.index); }
+        }
+        DG_REQUIRE(flat.size() <= cap, "buffer too small");
+        memcpy(out, flat.data(), flat.size() * 8);
+        *written = flat.size();
+    });
+}
+int dg_host_periodic_tables(uint8_t *out16) {
+    return guarded([&] { std::vector<fe> t = fs::periodic_tables(); memcpy(out16, t.data(), t.size() * 16); });
+}
 
 }  // extern "C"

@@ -106,6 +106,19 @@ int dg_dev_hash_rows(const void *d_ext, uint32_t width, uint32_t log_n, uint32_t
 /* writes > L2-size scratch to evict the L2 between timed iterations */
 int dg_dev_flush_l2(void);
 
+/* ---- host-side Fiat-Shamir glue, exported so that it can be unit-tested without a GPU (none of these touch the device) ---- */
+/* field::prng_vector (field.rs:271-275): count draws of StdRng::from_seed(seed) through Uniform(0..M) */
+int dg_host_prng_vector(const uint8_t seed[32], uint64_t count, uint8_t *out16);
+/* utils::compute_query_positions (stark/utils/mod.rs:25-44) */
+int dg_host_query_positions(const uint8_t seed[32], uint64_t domain_size, uint32_t extension_factor, uint32_t num_queries, uint64_t *out);
+/* blake3 of a message of at most 1024 bytes (the FRI-roots seed of prover.rs:119-127) */
+int dg_host_blake3(const uint8_t *data, size_t len, uint8_t out32[32]);
+/* MerkleTree::prove_batch planning (merkle.rs:64-124): writes, per normalised slot, the count and then (is_leaf, index) pairs;
+ * out layout: [n_slots][depth] then for each slot [count] (is_leaf, index)*count, all uint64 */
+int dg_host_plan_batch(const uint64_t *indexes, uint32_t n_indexes, uint64_t n_leaves, uint64_t *out, size_t cap, size_t *written);
+/* extend_constants tables (constraints/utils.rs:87-113): 128 rows x 23 columns = sponge ARK 8 | masks 3 | hasher ARK 12 */
+int dg_host_periodic_tables(uint8_t *out16 /* 128*23 elements */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,126 @@
+"""CPU-side tests of the product's host logic (distaff_b200/csrc/host_fs.cu, exported as dg_host_*) against the oracle:
+Fiat-Shamir draws, query positions, seed hashing, batch-proof planning and the periodic constant tables.  No GPU needed."""
+import ctypes
+import os
+import struct
+
+import numpy as np
+import pytest
+
+M = 2**128 - 45 * 2**40 + 1
+
+
+@pytest.fixture(scope="module")
+def L():
+    from distaff_b200 import backend
+    if not os.path.exists(backend.LIB_PATH):
+        pytest.skip("libdistaff_gpu.so not built")
+    return backend.lib()
+
+
+def test_prng_vector_matches_oracle(L, po):
+    from distaff_b200 import felt
+    for seed in (bytes(range(32)), bytes([7] * 32), bytes(32)):
+        out = np.zeros((600, 2), dtype=np.uint64)
+        assert L.dg_host_prng_vector(seed, 600, out.ctypes.data) == 0
+        assert felt.to_ints(out) == po.prng_vector(seed, 600)
+    assert felt.to_ints(out[:1])[0] < M
+
+
+def test_query_positions_match_oracle(L, po):
+    for seed, domain, ext, nq in ((bytes(range(32)), 2**13, 32, 50), (bytes([3] * 32), 2**25, 32, 50), (bytes([9] * 32), 2**10, 16, 128)):
+        out = np.zeros(nq, dtype=np.uint64)
+        assert L.dg_host_query_positions(seed, domain, ext, nq, out.ctypes.data) == 0
+        assert [int(x) for x in out] == po.query_positions(seed, domain, ext, nq)
+    out = np.zeros(64, dtype=np.uint64)
+    assert L.dg_host_query_positions(bytes(32), 64, 32, 64, out.ctypes.data) == -4      # cannot find 64 positions: utils/mod.rs:39-41
+
+
+def test_short_blake3_matches_oracle(L, po):
+    data = bytes((i * 7 + 1) % 256 for i in range(1024))
+    for n in (0, 1, 32, 63, 64, 65, 320, 352, 1023, 1024):
+        out = ctypes.create_string_buffer(32)
+        assert L.dg_host_blake3(data[:n], n, out) == 0
+        assert out.raw == po.hash("blake3", data[:n])
+    assert L.dg_host_blake3(data + b"x", 1025, out) != 0
+
+
+def _oracle_plan(po, leaves, indexes):
+    """structure of the oracle's prove_batch: per slot the list of 32-byte nodes"""
+    raw = po.merkle_prove_batch("blake3", leaves, indexes)
+    off = 0
+
+    def u64():
+        nonlocal off
+        v = struct.unpack_from("<Q", raw, off)[0]
+        off += 8
+        return v
+    nv = u64()
+    off += 32 * nv
+    slots = []
+    for _ in range(u64()):
+        k = u64()
+        slots.append([raw[off + 32 * i: off + 32 * i + 32] for i in range(k)])
+        off += 32 * k
+    return slots, raw[off]
+
+
+def test_batch_proof_plan_matches_oracle_structure(L, po):
+    rng = np.random.Generator(np.random.PCG64(5))
+    for log_l in (3, 6, 10):
+        n = 1 << log_l
+        leaves = rng.integers(0, 256, size=n * 32, dtype=np.uint8).tobytes()
+        nodes = po.merkle_nodes("blake3", leaves)
+        for trial in range(6):
+            k = int(rng.integers(1, min(n, 40) + 1))
+            idx = [int(x) for x in rng.choice(n, size=k, replace=False)]
+            want, depth = _oracle_plan(po, leaves, idx)
+            arr = np.array(idx, dtype=np.uint64)
+            out = np.zeros(4096, dtype=np.uint64)
+            written = ctypes.c_size_t(0)
+            assert L.dg_host_plan_batch(arr.ctypes.data, k, n, out.ctypes.data, 4096, ctypes.byref(written)) == 0
+            flat = [int(x) for x in out[:written.value]]
+            n_slots, d = flat[0], flat[1]
+            assert d == depth and n_slots == len(want)
+            pos = 2
+            for s in range(n_slots):
+                cnt = flat[pos]
+                pos += 1
+                got = []
+                for _ in range(cnt):
+                    is_leaf, index = flat[pos], flat[pos + 1]
+                    pos += 2
+                    src = leaves if is_leaf else nodes
+                    got.append(src[32 * index: 32 * index + 32])
+                assert got == want[s], (log_l, idx, s)
+    arr = np.array([1, 1], dtype=np.uint64)
+    assert L.dg_host_plan_batch(arr.ctypes.data, 2, 8, out.ctypes.data, 4096, ctypes.byref(written)) != 0     # repeating indexes (merkle.rs:302)
+
+
+def test_periodic_tables_interpolate_the_round_constants(L):
+    # rows 0, 8, 16, ... of the 8x-extended cycle are the original 16 round constants; masks are 0/1 there
+    from distaff_b200 import felt
+    out = np.zeros((128 * 23, 2), dtype=np.uint64)
+    assert L.dg_host_periodic_tables(out.ctypes.data) == 0
+    t = np.array(felt.to_ints(out), dtype=object).reshape(128, 23)
+    masks = [[0] + [1] * 15, [1] * 15 + [0], [0] + [1] * 7 + [0] + [1] * 7]
+    for m in range(3):
+        assert [int(t[8 * k, 8 + m]) for k in range(16)] == masks[m]
+    assert all(0 <= int(v) < M for v in t.reshape(-1))
+    # the extension is a degree < 16 polynomial: check one column against Lagrange evaluation through Python big ints
+    G = 23953097886125630542083529559205016746
+    w128 = pow(G, 2**40 // 128, M)
+    xs = [pow(w128, 8 * k, M) for k in range(16)]
+    col = 3
+    ys = [int(t[8 * k, col]) for k in range(16)]
+    for s in (1, 5, 77, 127):
+        x = pow(w128, s, M)
+        acc = 0
+        for i in range(16):
+            num, den = 1, 1
+            for j in range(16):
+                if i != j:
+                    num = num * (x - xs[j]) % M
+                    den = den * (xs[i] - xs[j]) % M
+            acc = (acc + ys[i] * num * pow(den, M - 2, M)) % M
+        assert acc == int(t[s, col])
