@@ -76,7 +76,8 @@ struct Acc {
     }
 };
 
-__global__ void __launch_bounds__(128) constraint_eval_kernel(const AirParams P) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const AirParams P) {
     const unsigned long long n = 1ULL << P.log_n;
     const unsigned long long E = n << 3;
     const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,29 +140,12 @@ __global__ void __launch_bounds__(128) constraint_eval_kernel(const AirParams P)
         cff[0] = fe_mul(a0, n2); cff[1] = fe_mul(a1, n2); cff[2] = fe_mul(a2, n2); cff[3] = fe_mul(a3, n2);
         cff[4] = fe_mul(a0, cf[2]); cff[5] = fe_mul(a1, cf[2]); cff[6] = fe_mul(a2, cf[2]); cff[7] = fe_mul(a3, cf[2]);
     }
-    {
-        fe n0 = bnot(ld[0]), n1 = bnot(ld[1]);
-        ldf[0] = fe_mul(n0, n1); ldf[1] = fe_mul(ld[0], n1);
-        ldf[2] = fe_mul(n0, cf[1]);                                   // sic (trace_state.rs:301)
-        ldf[3] = fe_mul(ld[0], ld[1]);
-        fe n2 = bnot(ld[2]);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { ldf[4 + i] = fe_mul(ldf[i], ld[2]); ldf[i] = fe_mul(ldf[i], n2); }
-        fe n3 = bnot(ld[3]);
-#pragma unroll
-        for (int i = 0; i < 8; i++) { ldf[8 + i] = fe_mul(ldf[i], ld[3]); ldf[i] = fe_mul(ldf[i], n3); }
-        fe n4 = bnot(ld[4]);
-#pragma unroll
-        for (int i = 0; i < 16; i++) { ldf[16 + i] = fe_mul(ldf[i], ld[4]); ldf[i] = fe_mul(ldf[i], n4); }
-    }
-    fe begin_flag, noop_flag;
+    fe hdf_raw0;
     {
         fe n0 = bnot(hd[0]), n1 = bnot(hd[1]);
         hdf[0] = fe_mul(n0, n1); hdf[1] = fe_mul(hd[0], n1); hdf[2] = fe_mul(n0, hd[1]); hdf[3] = fe_mul(hd[0], hd[1]);
-        begin_flag = fe_mul(ldf[0], hdf[0]);
-        noop_flag = fe_mul(ldf[31], hdf[3]);
+        hdf_raw0 = hdf[0];
         hdf[0] = fe_mul(hdf[0], ld[0]);      // PUSH flag adjustment
-        ldf[0] = fe_mul(ldf[0], hd[0]);      // ASSERT flag adjustment
     }
     fe next_void;
     {
@@ -277,6 +261,27 @@ __global__ void __launch_bounds__(128) constraint_eval_kernel(const AirParams P)
         }
     }
 
+    {
+        fe n0 = bnot(ld[0]), n1 = bnot(ld[1]);
+        ldf[0] = fe_mul(n0, n1); ldf[1] = fe_mul(ld[0], n1);
+        ldf[2] = fe_mul(n0, cf[1]);                                   // sic (trace_state.rs:301)
+        ldf[3] = fe_mul(ld[0], ld[1]);
+        fe n2 = bnot(ld[2]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { ldf[4 + i] = fe_mul(ldf[i], ld[2]); ldf[i] = fe_mul(ldf[i], n2); }
+        fe n3 = bnot(ld[3]);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { ldf[8 + i] = fe_mul(ldf[i], ld[3]); ldf[i] = fe_mul(ldf[i], n3); }
+        fe n4 = bnot(ld[4]);
+#pragma unroll
+        for (int i = 0; i < 16; i++) { ldf[16 + i] = fe_mul(ldf[i], ld[4]); ldf[i] = fe_mul(ldf[i], n4); }
+    }
+    fe begin_flag, noop_flag;
+    {
+        begin_flag = fe_mul(ldf[0], hdf_raw0);
+        noop_flag = fe_mul(ldf[31], hdf[3]);
+        ldf[0] = fe_mul(ldf[0], hd[0]);      // ASSERT flag adjustment
+    }
     // ---- stack constraints (stack/mod.rs:117-195) -----------------------------------------------------------------------------------
     {
         const int base = 20 + cl + ll;       // aux constraints at base, base+1; stack slots from base+2
@@ -469,7 +474,17 @@ __global__ void __launch_bounds__(128) constraint_eval_kernel(const AirParams P)
 void launch_constraint_eval(Context &c, const AirParams &P) {
     air_upload_constants();
     const unsigned long long E = 8ULL << P.log_n;
-    constraint_eval_kernel<<<(unsigned)((E + 127) / 128), 128, 0, c.stream>>>(P); c.launches++;
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("DG_AIR_LB"); variant = e ? atoi(e) : 4; }   // 4 blocks/SM (128 registers, some local spills) measured fastest on B200
+    const unsigned grid = (unsigned)((E + 127) / 128);
+    switch (variant) {
+        case 2: constraint_eval_kernel<2><<<grid, 128, 0, c.stream>>>(P); break;
+        case 3: constraint_eval_kernel<3><<<grid, 128, 0, c.stream>>>(P); break;
+        case 5: constraint_eval_kernel<5><<<grid, 128, 0, c.stream>>>(P); break;
+        case 6: constraint_eval_kernel<6><<<grid, 128, 0, c.stream>>>(P); break;
+        default: constraint_eval_kernel<4><<<grid, 128, 0, c.stream>>>(P); break;
+    }
+    c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 

@@ -62,7 +62,11 @@ __global__ void field_op_kernel(int op, int impl, const fe *a, const fe *b, fe *
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fe x = a[i], y = b ? b[i] : fe_make(0, 0), r;
-    if (impl == 0) {
+    if (impl == 2 && op == 2) {
+#ifdef __CUDA_ARCH__
+        r = ptx::fe_mul_v1(x, y);
+#endif
+    } else if (impl == 0) {
         switch (op) {
             case 0: r = fe_add(x, y); break;
             case 1: r = fe_sub(x, y); break;

@@ -82,6 +82,8 @@ struct Context {
     unsigned long long launches = 0;        // kernels launched by this library (bench.py's gpu_launches)
 
     TwiddleRef twiddle(int log_order, bool inverse);
+    std::map<int, DevBuf> single_tables;    // full power tables w^e, e < 2^log_order (small orders only)
+    const fe *single_table(int log_order);
     const fe *roots(int log_l, bool inverse) const { return small_roots[inverse ? 1 : 0].as<fe>() + small_root_offset[log_l]; }
 };
 

@@ -50,17 +50,25 @@ static void build_context(int device) {
         DG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
     }
     // small root tables
+    // per-stage tables of every sub-transform size L = 2^l: stage st occupies [L - (L >> st), L - (L >> (st+1))) with
+    // W_st[j] = w_L^(j << st), j < L >> (st+1); L entries reserved per size (the last one is unused)
     size_t total = 0;
-    for (int l = 1; l <= MAX_LOG_L; l++) { c->small_root_offset[l] = total; total += (size_t)1 << (l - 1); }
+    for (int l = 1; l <= MAX_LOG_L; l++) { c->small_root_offset[l] = total; total += (size_t)1 << l; }
     c->small_root_offset[0] = 0;
     for (int inv = 0; inv < 2; inv++) {
         c->small_roots[inv].alloc(total * sizeof(fe));
+        DG_CUDA(cudaMemsetAsync(c->small_roots[inv].p, 0, total * sizeof(fe), c->stream));
         for (int l = 1; l <= MAX_LOG_L; l++) {
             fe w = host_root_of_unity(l);
             if (inv) w = host_inv(w);
-            unsigned cnt = 1u << (l - 1);
-            power_table_kernel<<<(cnt + 127) / 128, 128, 0, c->stream>>>(c->small_roots[inv].as<fe>() + c->small_root_offset[l], w, cnt);
-            DG_CUDA(cudaGetLastError());
+            const unsigned L = 1u << l;
+            for (int st = 0; st < l; st++) {
+                unsigned cnt = L >> (st + 1);
+                fe *out = c->small_roots[inv].as<fe>() + c->small_root_offset[l] + (L - (L >> st));
+                power_table_kernel<<<(cnt + 127) / 128, 128, 0, c->stream>>>(out, w, cnt);
+                DG_CUDA(cudaGetLastError());
+                w = fe_sqr(w);
+            }
         }
     }
     DG_CUDA(cudaStreamSynchronize(c->stream));
@@ -83,6 +91,19 @@ void ctx_init(int device) {
 Context &ctx() {
     ctx_init(-1);
     return *g_ctx;
+}
+
+const fe *Context::single_table(int log_order) {
+    DG_REQUIRE(log_order <= 20, "single-level table too large");
+    auto it = single_tables.find(log_order);
+    if (it == single_tables.end()) {
+        DevBuf t(((size_t)1 << log_order) * sizeof(fe));
+        const unsigned cnt = 1u << log_order;
+        power_table_kernel<<<(cnt + 127) / 128, 128, 0, stream>>>(t.as<fe>(), host_root_of_unity(log_order), cnt); launches++;
+        DG_CUDA(cudaGetLastError());
+        it = single_tables.emplace(log_order, std::move(t)).first;
+    }
+    return it->second.as<fe>();
 }
 
 TwiddleRef Context::twiddle(int log_order, bool inverse) {

@@ -207,7 +207,7 @@ __device__ __forceinline__ fe fe_reduce256(unsigned long long t0, unsigned long 
     return r;
 }
 
-__device__ __forceinline__ fe fe_mul(fe a, fe b) {
+__device__ __forceinline__ fe fe_mul_v1(fe a, fe b) {
     unsigned int x[4] = { (unsigned int)a.lo, (unsigned int)(a.lo >> 32), (unsigned int)a.hi, (unsigned int)(a.hi >> 32) };
     unsigned int y[4] = { (unsigned int)b.lo, (unsigned int)(b.lo >> 32), (unsigned int)b.hi, (unsigned int)(b.hi >> 32) };
     unsigned int r[8];
@@ -216,6 +216,120 @@ __device__ __forceinline__ fe fe_mul(fe a, fe b) {
                         ((unsigned long long)r[5] << 32) | r[4], ((unsigned long long)r[7] << 32) | r[6]);
 }
 
+// 256-bit product with separate even-column / odd-column 64-bit accumulators: every (lo, hi) pair below is a dedicated
+// register pair, so ptxas fuses each mad.lo/madc.hi couple into one IMAD.WIDE.U32 (carry-out / .X carry-in forms) without
+// the register shuffles that overlapping pairs cause.  E = columns 0,2,4,6 ; O = columns 1,3,5,7.
+__device__ __forceinline__ void mul_wide_eo(const unsigned int a[4], const unsigned int b[4], unsigned int r[8]) {
+    unsigned int e0, e1, e2, e3, e4, e5, e6, e7, o1, o2, o3, o4, o5, o6, o7;
+    // row 0: E0 = a0 b0, E2 = a0 b2, O1 = a0 b1, O3 = a0 b3
+    asm("mul.lo.u32 %0, %8, %9;\n\t"  "mul.hi.u32 %1, %8, %9;\n\t"
+        "mul.lo.u32 %2, %8, %11;\n\t" "mul.hi.u32 %3, %8, %11;\n\t"
+        "mul.lo.u32 %4, %8, %10;\n\t" "mul.hi.u32 %5, %8, %10;\n\t"
+        "mul.lo.u32 %6, %8, %12;\n\t" "mul.hi.u32 %7, %8, %12;"
+        : "=&r"(e0), "=&r"(e1), "=&r"(e2), "=&r"(e3), "=&r"(o1), "=&r"(o2), "=&r"(o3), "=&r"(o4)
+        : "r"(a[0]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+    // row 1: O1 += a1 b0 ; O3 += a1 b2 + c ; O5 = c        E2 += a1 b1 ; E4 = a1 b3 + c
+    asm("mad.lo.cc.u32  %0, %9, %10, %0;\n\t"  "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"  "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "addc.u32       %4, 0, 0;\n\t"
+        "mad.lo.cc.u32  %5, %9, %11, %5;\n\t"  "madc.hi.cc.u32 %6, %9, %11, %6;\n\t"
+        "madc.lo.cc.u32 %7, %9, %13, 0;\n\t"   "madc.hi.u32    %8, %9, %13, 0;"
+        : "+r"(o1), "+r"(o2), "+r"(o3), "+r"(o4), "=&r"(o5), "+r"(e2), "+r"(e3), "=&r"(e4), "=&r"(e5)
+        : "r"(a[1]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+    // row 2: E2 += a2 b0 ; E4 += a2 b2 + c ; E6 = c        O3 += a2 b1 ; O5:O6 = a2 b3 + O5 + c
+    asm("mad.lo.cc.u32  %0, %9, %10, %0;\n\t" "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t" "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "addc.u32       %4, 0, 0;\n\t"
+        "mad.lo.cc.u32  %5, %9, %11, %5;\n\t" "madc.hi.cc.u32 %6, %9, %11, %6;\n\t"
+        "madc.lo.cc.u32 %7, %9, %13, %7;\n\t" "madc.hi.u32    %8, %9, %13, 0;"
+        : "+r"(e2), "+r"(e3), "+r"(e4), "+r"(e5), "=&r"(e6), "+r"(o3), "+r"(o4), "+r"(o5), "=&r"(o6)
+        : "r"(a[2]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+    // row 3: O3 += a3 b0 ; O5 += a3 b2 + c ; O7 = c        E4 += a3 b1 ; E6:E7 = a3 b3 + E6 + c
+    asm("mad.lo.cc.u32  %0, %9, %10, %0;\n\t" "madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t" "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
+        "addc.u32       %4, 0, 0;\n\t"
+        "mad.lo.cc.u32  %5, %9, %11, %5;\n\t" "madc.hi.cc.u32 %6, %9, %11, %6;\n\t"
+        "madc.lo.cc.u32 %7, %9, %13, %7;\n\t" "madc.hi.u32    %8, %9, %13, 0;"
+        : "+r"(o3), "+r"(o4), "+r"(o5), "+r"(o6), "=&r"(o7), "+r"(e4), "+r"(e5), "+r"(e6), "=&r"(e7)
+        : "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]));
+    // result = E + (O << 32)
+    r[0] = e0;
+    asm("add.cc.u32  %0, %7, %14;\n\t"
+        "addc.cc.u32 %1, %8, %15;\n\t"
+        "addc.cc.u32 %2, %9, %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t"
+        "addc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32    %6, %13, %20;"
+        : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
+        : "r"(e1), "r"(e2), "r"(e3), "r"(e4), "r"(e5), "r"(e6), "r"(e7), "r"(o1), "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6), "r"(o7));
+}
+
+// ---- variant 3: reduction built from IMAD.WIDE chains (FMA pipe) instead of 64-bit add/shift sequences (ALU pipe) --------------
+//   hi*C = ((hi * 45*2^8) << 32) - hi ;  the "<< 32" is a limb rename, the additions of the low limbs ride on the wide
+//   multiply-adds (multiplier 1), so the only ALU work left is two borrow chains and the final canonicalisation.
+#define DG_HAVE_V3 1
+__device__ __forceinline__ unsigned long long wmad(unsigned int a, unsigned int b, unsigned long long c) {
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ fe fe_reduce_v3(const unsigned int r[8]) {
+    const unsigned int K = 11520u;   // 45 * 2^8
+    // V = lo + ((hi * K) << 32)   (6 limbs)
+    unsigned long long t0 = wmad(r[4], K, (unsigned long long)r[1]);
+    unsigned long long t1 = wmad(r[2], 1u, wmad(r[5], K, t0 >> 32));
+    unsigned long long t2 = wmad(r[3], 1u, wmad(r[6], K, t1 >> 32));
+    unsigned long long t3 = wmad(r[7], K, t2 >> 32);
+    unsigned int v0 = r[0], v1 = (unsigned int)t0, v2 = (unsigned int)t1, v3 = (unsigned int)t2, v4 = (unsigned int)t3, v5 = (unsigned int)(t3 >> 32);
+    // V -= hi
+    asm("sub.cc.u32  %0, %0, %6;\n\t"
+        "subc.cc.u32 %1, %1, %7;\n\t"
+        "subc.cc.u32 %2, %2, %8;\n\t"
+        "subc.cc.u32 %3, %3, %9;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t"
+        "subc.u32    %5, %5, 0;"
+        : "+r"(v0), "+r"(v1), "+r"(v2), "+r"(v3), "+r"(v4), "+r"(v5) : "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+    // fold the 47-bit top T = v5:v4 :  T*C = ((T*K) << 32) - T ;  T*K < 2^61
+    unsigned long long w0 = wmad(v4, K, 0ULL);
+    unsigned long long w1 = wmad(v5, K, w0 >> 32);
+    unsigned int a1 = (unsigned int)w0, a2 = (unsigned int)w1, a3 = (unsigned int)(w1 >> 32);
+    unsigned int cy, bw;
+    asm("add.cc.u32  %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.u32    %3, 0, 0;\n\t"
+        "sub.cc.u32  %4, %4, %8;\n\t"
+        "subc.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.u32    %3, %3, 0;"
+        : "+r"(v1), "+r"(v2), "+r"(v3), "=&r"(cy), "+r"(v0) : "r"(a1), "r"(a2), "r"(a3), "r"(v4), "r"(v5));
+    // cy is now carry - borrow in {0, 1} (the value is non-negative and < 2^128 + 2^93)
+    (void)bw;
+    // canonical form: q = r + C; take q when r overflowed 2^128 or r >= M
+    unsigned int q0, q1, q2, q3, g;
+    asm("add.cc.u32  %0, %5, 0xffffffff;\n\t"
+        "addc.cc.u32 %1, %6, 0x00002cff;\n\t"
+        "addc.cc.u32 %2, %7, 0;\n\t"
+        "addc.cc.u32 %3, %8, 0;\n\t"
+        "addc.u32    %4, 0, 0;"
+        : "=&r"(q0), "=&r"(q1), "=&r"(q2), "=&r"(q3), "=&r"(g) : "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+    const bool use_q = (cy | g) != 0;
+    fe out;
+    out.lo = ((unsigned long long)(use_q ? q1 : v1) << 32) | (use_q ? q0 : v0);
+    out.hi = ((unsigned long long)(use_q ? q3 : v3) << 32) | (use_q ? q2 : v2);
+    return out;
+}
+__device__ __forceinline__ fe fe_mul_v3(fe a, fe b) {
+    unsigned int x[4] = { (unsigned int)a.lo, (unsigned int)(a.lo >> 32), (unsigned int)a.hi, (unsigned int)(a.hi >> 32) };
+    unsigned int y[4] = { (unsigned int)b.lo, (unsigned int)(b.lo >> 32), (unsigned int)b.hi, (unsigned int)(b.hi >> 32) };
+    unsigned int r[8];
+    mul_wide_eo(x, y, r);
+    return fe_reduce_v3(r);
+}
+// the multiply used by every kernel (tools/bench_modmul.cu: 274 G modmul/s on B200 vs 228 for v1)
+__device__ __forceinline__ fe fe_mul(fe a, fe b) { return fe_mul_v3(a, b); }
 __device__ __forceinline__ fe fe_sqr(fe a) { return fe_mul(a, a); }
 
 // multiply by a small constant (< 2^32)

@@ -34,7 +34,11 @@ struct PassGeom {
     int fold;
     long long fold_stride;
     TwiddleRef cw;
-    const fe *roots;                    // w_L^m, m < L/2
+    int coset_fast;                     // fold == 1: input factor from a single-level table, lane factor merged into the output twiddle
+    const fe *cw_point;                 // cw_point[e] = (w_N^in_point)^e, e < cw_point_mask + 1
+    unsigned cw_point_mask;
+    int log_blowup;
+    const fe *roots;                    // per-stage twiddle tables of the L-point transform: W_st[j] = w_L^(j << st), back to back
 };
 
 __device__ __forceinline__ fe tw_lookup(const TwiddleRef &t, unsigned long long e) {
@@ -44,100 +48,162 @@ __device__ __forceinline__ fe tw_lookup(const TwiddleRef &t, unsigned long long 
     return fe_mul(a, b);
 }
 
-template <int LOG_L>
-__global__ void __launch_bounds__(256) ntt_pass_kernel(const fe *__restrict__ src, fe *__restrict__ dst, const PassGeom g) {
+// ---- pass kernel -------------------------------------------------------------------------------------------------------
+// One block transforms a tile of T lanes x L points.  The log2(L) decimation-in-frequency stages are grouped into rounds of
+// up to 4 stages that run entirely in registers on 2^rho elements per thread ("unit"); shared memory is touched only
+// between rounds.  The first round reads its operands straight from global memory and the last one writes straight back,
+// so a 1024-point sub-transform costs 2 shared-memory round trips and 2 barriers instead of 10.  Stage twiddles come from
+// per-stage compact tables W_st[j] = w_L^(j << st) (unit-stride, conflict-free) staged in shared memory.
+template <int LOG_L> struct Rounds {
+    static constexpr int R1 = LOG_L <= 4 ? LOG_L : 4;
+    static constexpr int REM = LOG_L - R1;
+    static constexpr int R2 = REM == 0 ? 0 : (REM <= 4 ? REM : (REM + 1) / 2);
+    static constexpr int R3 = REM - R2;
+};
+
+template <int LOG_L, int S0, int RHO>
+__device__ __forceinline__ void dif_regs(fe *x, const fe *s_tw, int g_lo) {
+    constexpr int L = 1 << LOG_L, R = 1 << RHO;
+    constexpr int LOG_SP = LOG_L - S0 - RHO;
+#pragma unroll
+    for (int u = 0; u < RHO; u++) {
+        const int hr = R >> (u + 1);
+        const int st = S0 + u;
+        const fe *W = s_tw + (L - (L >> st));
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            if ((i & hr) == 0) {
+                fe a = x[i], b = x[i + hr];
+                x[i] = fe_add(a, b);
+                fe d = fe_sub(a, b);
+                // in the last round (LOG_SP == 0, g_lo == 0) the twiddle index is a compile-time constant: index 0 is w^0 = 1
+                if (st != LOG_L - 1 && !(LOG_SP == 0 && (i & (hr - 1)) == 0)) d = fe_mul(d, W[g_lo + ((i & (hr - 1)) << LOG_SP)]);
+                x[i + hr] = d;
+            }
+        }
+    }
+}
+
+template <int LOG_L, bool LANE_MAJOR>
+__device__ __forceinline__ int sidx(int pos, int t, int T) {
+    constexpr int L = 1 << LOG_L;
+    constexpr int LS = L + (L >> 3) + 1;                 // padded lane stride, one pad element per 8 points
+    return LANE_MAJOR ? (t * LS + pos + (pos >> 3)) : (pos * T + t);
+}
+
+template <int LOG_L, int S0, int RHO, bool FIRST, bool LAST, bool LANE_MAJOR>
+__device__ __forceinline__ void ntt_round(const fe *__restrict__ src, fe *__restrict__ dst, fe *s_data, const fe *s_tw, const PassGeom &g,
+                                          unsigned tile, long long in_base) {
+    constexpr int L = 1 << LOG_L, R = 1 << RHO;
+    constexpr int LOG_B = LOG_L - S0, LOG_SP = LOG_B - RHO;
+    constexpr int N_GLO = 1 << LOG_SP, N_GHI = 1 << S0;
+    const int T = 1 << g.log_t;
+    const int units = (L >> RHO) * T;
+    for (int u = threadIdx.x; u < units; u += blockDim.x) {
+        int t, g_lo, g_hi;
+        if (!LANE_MAJOR || LAST) {             // lanes fastest: global accesses of neighbouring threads are contiguous across lanes
+            t = u & (T - 1);
+            const int rest = u >> g.log_t;
+            g_lo = rest & (N_GLO - 1);
+            g_hi = rest >> LOG_SP;
+        } else {                               // points fastest: contiguous rows of the last pass / conflict-free shared accesses
+            g_lo = u & (N_GLO - 1);
+            const int rest = u >> LOG_SP;
+            g_hi = rest & (N_GHI - 1);
+            t = rest >> S0;
+        }
+        const int gbase = (g_hi << LOG_B) + g_lo;
+        fe x[R];
+#pragma unroll
+        for (int m = 0; m < R; m++) {
+            const int pos = gbase + (m << LOG_SP);
+            if (FIRST) {
+                const long long j = in_base + (long long)t * g.in_lane + (long long)pos * g.in_point;
+                if (g.coset_fast) {
+                    // p[j] * w_N^(c*pos*in_point); the lane part w_N^(c*lane) rides on the output twiddle
+                    x[m] = fe_mul(src[j], g.cw_point[((unsigned)blockIdx.y * (unsigned)pos) & g.cw_point_mask]);
+                } else if (g.coset_on) {
+                    const unsigned long long c = blockIdx.y;
+                    fe v = fe_make(0, 0);
+                    for (int f = 0; f < g.fold; f++) {
+                        const long long jj = j + (long long)f * g.fold_stride;
+                        v = fe_add(v, fe_mul(src[jj], tw_lookup(g.cw, c * (unsigned long long)jj)));
+                    }
+                    x[m] = v;
+                } else {
+                    x[m] = src[j];
+                }
+            } else {
+                x[m] = s_data[sidx<LOG_L, LANE_MAJOR>(pos, t, T)];
+            }
+        }
+        dif_regs<LOG_L, S0, RHO>(x, s_tw, g_lo);
+#pragma unroll
+        for (int m = 0; m < R; m++) {
+            const int pos = gbase + (m << LOG_SP);
+            if (LAST) {                        // position q holds X[bitrev(q)]
+                const unsigned k = __brev((unsigned)pos) >> (32 - LOG_L);
+                fe v = x[m];
+                if (g.coset_fast && g.tw_on) v = fe_mul(v, tw_lookup(g.cw, (unsigned long long)(tile * T + t) * (((unsigned long long)k << g.log_blowup) + blockIdx.y)));
+                else if (g.tw_on) v = fe_mul(v, tw_lookup(g.tw, (unsigned long long)(tile * T + t) * k));
+                if (g.has_scale) v = fe_mul(v, g.scale);
+                dst[(long long)t * g.out_lane + (long long)k * g.out_point] = v;
+            } else {
+                s_data[sidx<LOG_L, LANE_MAJOR>(pos, t, T)] = x[m];
+            }
+        }
+    }
+}
+
+template <int LOG_L, bool LANE_MAJOR>
+__global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const fe *__restrict__ src, fe *__restrict__ dst, const PassGeom g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int L = 1 << LOG_L;
-    fe *s_roots = reinterpret_cast<fe *>(smem_raw);
-    fe *s = s_roots + (L / 2 > 0 ? L / 2 : 1);
+    typedef Rounds<LOG_L> RD;
+    fe *s_tw = reinterpret_cast<fe *>(smem_raw);          // L entries: per-stage tables back to back
+    fe *s_data = s_tw + L;
     const int T = 1 << g.log_t;
-    const int tid = threadIdx.x, nthreads = blockDim.x;
     const unsigned tile = blockIdx.x % g.num_tiles, outer = blockIdx.x / g.num_tiles;
     const long long in_base = (long long)outer * g.in_outer + (long long)tile * T * g.in_lane;   // index inside the vector
     src += (long long)blockIdx.y * g.in_batch_y + (long long)blockIdx.z * g.in_batch_z;
     dst += (long long)blockIdx.y * g.out_batch_y + (long long)blockIdx.z * g.out_batch_z + (long long)outer * g.out_outer +
            (long long)tile * T * g.out_lane;
-    const int ps = g.lane_major ? 1 : T;
-    const int ls = g.lane_major ? (L + 1) : 1;
-
-    for (int i = tid; i < L / 2; i += nthreads) s_roots[i] = g.roots[i];
-
-    // ---- load tile (optionally applying the coset transform of the LDE)
-    for (int e = tid; e < L * T; e += nthreads) {
-        int t, p;
-        if (g.lane_major) { p = e & (L - 1); t = e >> LOG_L; }
-        else { t = e & (T - 1); p = e >> g.log_t; }
-        long long j = in_base + (long long)t * g.in_lane + (long long)p * g.in_point;
-        fe v;
-        if (g.coset_on) {
-            const unsigned long long c = blockIdx.y;
-            v = fe_make(0, 0);
-            for (int f = 0; f < g.fold; f++) {
-                long long jj = j + (long long)f * g.fold_stride;
-                fe x = src[jj];
-                v = fe_add(v, fe_mul(x, tw_lookup(g.cw, c * (unsigned long long)jj)));
-            }
-        } else {
-            v = src[j];
-        }
-        s[p * ps + t * ls] = v;
-    }
+    for (int i = threadIdx.x; i < L - 1; i += blockDim.x) s_tw[i] = g.roots[i];
     __syncthreads();
-
-    // ---- L-point decimation-in-frequency transform per lane (natural in, bit-reversed out)
-#pragma unroll 1
-    for (int st = 0; st < LOG_L; st++) {
-        const int half = L >> (st + 1);
-        for (int b = tid; b < (L / 2) * T; b += nthreads) {
-            int t, q;
-            if (g.lane_major) { q = b & (L / 2 - 1); t = b >> (LOG_L - 1); }
-            else { t = b & (T - 1); q = b >> g.log_t; }
-            const int j = q & (half - 1);
-            const int i0 = ((q - j) << 1) + j;
-            fe *p0 = s + i0 * ps + t * ls;
-            fe *p1 = p0 + half * ps;
-            fe a = *p0, bb = *p1;
-            *p0 = fe_add(a, bb);
-            fe d = fe_sub(a, bb);
-            if (half > 1) d = fe_mul(d, s_roots[j << st]);
-            *p1 = d;
-        }
+    ntt_round<LOG_L, 0, RD::R1, true, RD::R2 == 0, LANE_MAJOR>(src, dst, s_data, s_tw, g, tile, in_base);
+    if constexpr (RD::R2 > 0) {
         __syncthreads();
+        ntt_round<LOG_L, RD::R1, RD::R2, false, RD::R3 == 0, LANE_MAJOR>(src, dst, s_data, s_tw, g, tile, in_base);
     }
-
-    // ---- store: position q holds X[bitrev(q)]
-    for (int e = tid; e < L * T; e += nthreads) {
-        const int t = e & (T - 1), q = e >> g.log_t;
-        const unsigned k = LOG_L == 0 ? 0u : (__brev((unsigned)q) >> (32 - (LOG_L == 0 ? 1 : LOG_L)));
-        fe v = s[q * ps + t * ls];
-        if (g.tw_on) v = fe_mul(v, tw_lookup(g.tw, (unsigned long long)(tile * T + t) * k));
-        if (g.has_scale) v = fe_mul(v, g.scale);
-        dst[(long long)t * g.out_lane + (long long)k * g.out_point] = v;
+    if constexpr (RD::R3 > 0) {
+        __syncthreads();
+        ntt_round<LOG_L, RD::R1 + RD::R2, RD::R3, false, true, LANE_MAJOR>(src, dst, s_data, s_tw, g, tile, in_base);
     }
 }
 
 typedef void (*PassKernel)(const fe *, fe *, const PassGeom);
-static PassKernel pass_kernel(int log_l) {
+template <bool LM> static PassKernel pass_kernel_t(int log_l) {
     switch (log_l) {
-        case 1: return ntt_pass_kernel<1>;  case 2: return ntt_pass_kernel<2>;  case 3: return ntt_pass_kernel<3>;
-        case 4: return ntt_pass_kernel<4>;  case 5: return ntt_pass_kernel<5>;  case 6: return ntt_pass_kernel<6>;
-        case 7: return ntt_pass_kernel<7>;  case 8: return ntt_pass_kernel<8>;  case 9: return ntt_pass_kernel<9>;
-        case 10: return ntt_pass_kernel<10>;
+        case 1: return ntt_pass_kernel<1, LM>;  case 2: return ntt_pass_kernel<2, LM>;  case 3: return ntt_pass_kernel<3, LM>;
+        case 4: return ntt_pass_kernel<4, LM>;  case 5: return ntt_pass_kernel<5, LM>;  case 6: return ntt_pass_kernel<6, LM>;
+        case 7: return ntt_pass_kernel<7, LM>;  case 8: return ntt_pass_kernel<8, LM>;  case 9: return ntt_pass_kernel<9, LM>;
+        case 10: return ntt_pass_kernel<10, LM>;
     }
     throw Error(-1, "unsupported sub-transform size");
 }
 
 static void launch_pass(Context &c, int log_l, PassGeom g, const fe *src, fe *dst, unsigned blocks_x, unsigned by, unsigned bz) {
     const int L = 1 << log_l, T = 1 << g.log_t;
-    size_t smem = (size_t)(L / 2 > 0 ? L / 2 : 1) * sizeof(fe) + (size_t)(g.lane_major ? T * (L + 1) : L * T) * sizeof(fe);
-    int threads = L * T / 2;
+    const size_t data = g.lane_major ? (size_t)T * (L + (L >> 3) + 1) : (size_t)L * T;
+    const size_t smem = ((size_t)L + data) * sizeof(fe);
+    int threads = L * T / 16;
     if (threads > 256) threads = 256;
     if (threads < 32) threads = 32;
-    PassKernel k = pass_kernel(log_l);
-    static bool attr_set[MAX_LOG_L + 1] = {false};
-    if (!attr_set[log_l]) {
+    PassKernel k = g.lane_major ? pass_kernel_t<true>(log_l) : pass_kernel_t<false>(log_l);
+    static bool attr_set[2][MAX_LOG_L + 1] = {{false}};
+    if (!attr_set[g.lane_major][log_l]) {
         DG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set[log_l] = true;
+        attr_set[g.lane_major][log_l] = true;
     }
     DG_REQUIRE(by <= 65535 && bz <= 65535, "batch too large for one launch");
     k<<<dim3(blocks_x, by, bz), threads, smem, c.stream>>>(src, dst, g); c.launches++;
@@ -179,6 +245,14 @@ static void run_transform(Context &c, const fe *src, fe *dst, int log_n, bool in
         base.fold = cs.fold;
         base.fold_stride = n;
         base.cw = c.twiddle(log_n + cs.log_blowup, false);
+        base.log_blowup = cs.log_blowup;
+        if (cs.fold == 1) {
+            // order of w_N^in_point where in_point = n / N1 (first pass) : N / in_point = N1 << log_blowup
+            const int log_order = l[0] + cs.log_blowup;
+            base.coset_fast = 1;
+            base.cw_point = c.single_table(log_order);
+            base.cw_point_mask = (1u << log_order) - 1u;
+        }
     }
 
     fe *tmp = nullptr;

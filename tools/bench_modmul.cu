@@ -1,0 +1,85 @@
+// Standalone micro-benchmark for fe_mul variants (throughput on independent chains + equality with the portable path).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I distaff_b200/csrc -o /tmp/bench_modmul tools/bench_modmul.cu && /tmp/bench_modmul
+#include <cstdio>
+#include <vector>
+#include <cuda_runtime.h>
+#include "fp128.cuh"
+using namespace dg;
+
+#define DG_HAVE_V3 1
+template <int V> __device__ __forceinline__ fe mulv(fe a, fe b) {
+#ifdef __CUDA_ARCH__
+    if (V == 1) return ptx::fe_mul_v1(a, b);
+    if (V == 2) return ptx::fe_mul_v3(a, b);
+#endif
+    return portable::fe_mul(a, b);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) tput(const fe *in, fe *out, int iters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    fe x0 = in[i], x1 = in[i + 1], x2 = in[i + 2], x3 = in[i + 3], m = in[i + 4];
+    for (int k = 0; k < iters; k++) { x0 = mulv<V>(x0, m); x1 = mulv<V>(x1, m); x2 = mulv<V>(x2, m); x3 = mulv<V>(x3, m); }
+    out[i] = fe_add(fe_add(x0, x1), fe_add(x2, x3));
+}
+// butterfly-like mix: add, sub, mul
+template <int V>
+__global__ void __launch_bounds__(256) tput_bfly(const fe *in, fe *out, int iters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    fe a = in[i], b = in[i + 1], c = in[i + 2], d = in[i + 3], w = in[i + 4];
+    for (int k = 0; k < iters; k++) {
+        fe s = fe_add(a, b), t = mulv<V>(fe_sub(a, b), w); a = s; b = t;
+        fe s2 = fe_add(c, d), t2 = mulv<V>(fe_sub(c, d), w); c = s2; d = t2;
+    }
+    out[i] = fe_add(fe_add(a, b), fe_add(c, d));
+}
+template <int V> __global__ void check(const fe *a, const fe *b, fe *o, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) o[i] = mulv<V>(a[i], b[i]); }
+
+template <int V> void run(const char *name, fe *d_in, fe *d_out, int blocks, int iters) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int kind = 0; kind < 2; kind++) {
+        float best = 1e9;
+        for (int rep = 0; rep < 3; rep++) {
+            cudaEventRecord(e0);
+            if (kind == 0) tput<V><<<blocks, 256>>>(d_in, d_out, iters); else tput_bfly<V><<<blocks, 256>>>(d_in, d_out, iters);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+        }
+        double ops = (double)blocks * 256 * iters * (kind == 0 ? 4 : 2);
+        printf("%-10s %-6s %8.3f ms  %7.1f G%s/s\n", name, kind == 0 ? "mul" : "bfly", best, ops / best / 1e6, kind == 0 ? "mul" : "bfly");
+    }
+}
+
+int main() {
+    const int blocks = 148 * 8, iters = 2000, n = blocks * 256 + 8;
+    std::vector<fe> h(n);
+    unsigned long long s = 88172645463325252ULL;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    for (auto &x : h) { x.lo = rnd(); x.hi = rnd(); if (x.hi == ~0ULL) x.hi = 12345; }
+    // edge cases at the front
+    const fe edge[] = {{0, 0}, {1, 0}, {DG_M_LO - 1, DG_M_HI}, {DG_M_LO - 2, DG_M_HI}, {~0ULL, 0}, {0, 1}, {0, 1ULL << 63}, {DG_C_LO, 0}, {DG_C_LO + 1, 0}, {0xffffffffULL, 0xffffffff00000000ULL}};
+    const int ne = sizeof(edge) / sizeof(edge[0]);
+    std::vector<fe> ea, eb;
+    for (int i = 0; i < ne; i++) for (int j = 0; j < ne; j++) { ea.push_back(edge[i]); eb.push_back(edge[j]); }
+    for (int i = 0; i < 200000; i++) { ea.push_back(h[i % n]); eb.push_back(h[(i * 7 + 3) % n]); }
+    fe *d_in, *d_out, *da, *db, *d0, *d1;
+    cudaMalloc(&d_in, n * 16); cudaMalloc(&d_out, n * 16);
+    cudaMemcpy(d_in, h.data(), n * 16, cudaMemcpyHostToDevice);
+    int m = ea.size();
+    cudaMalloc(&da, m * 16); cudaMalloc(&db, m * 16); cudaMalloc(&d0, m * 16); cudaMalloc(&d1, m * 16);
+    cudaMemcpy(da, ea.data(), m * 16, cudaMemcpyHostToDevice); cudaMemcpy(db, eb.data(), m * 16, cudaMemcpyHostToDevice);
+    std::vector<fe> r0(m), r1(m);
+    check<0><<<(m + 255) / 256, 256>>>(da, db, d0, m); cudaMemcpy(r0.data(), d0, m * 16, cudaMemcpyDeviceToHost);
+    auto cmp = [&](const char *nm) { cudaMemcpy(r1.data(), d1, m * 16, cudaMemcpyDeviceToHost); int bad = 0; for (int i = 0; i < m; i++) if (r0[i].lo != r1[i].lo || r0[i].hi != r1[i].hi) { if (bad < 3) printf("  %s mismatch at %d\n", nm, i); bad++; } printf("%s vs portable: %d mismatches of %d\n", nm, bad, m); };
+    check<1><<<(m + 255) / 256, 256>>>(da, db, d1, m); cmp("ptx");
+#ifdef DG_HAVE_V3
+    check<2><<<(m + 255) / 256, 256>>>(da, db, d1, m); cmp("v3");
+#endif
+    run<0>("portable", d_in, d_out, blocks, iters);
+    run<1>("ptx", d_in, d_out, blocks, iters);
+#ifdef DG_HAVE_V3
+    run<2>("v3", d_in, d_out, blocks, iters);
+#endif
+    printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+}
