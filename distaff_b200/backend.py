@@ -60,6 +60,10 @@ EXPORTS = {
     "dg_dev_merkle_build": [vp, u64, vp, fp],
     "dg_dev_hash_rows": [vp, u32, u32, u32, vp, fp],
     "dg_dev_flush_l2": [],
+    "dg_comm_unique_id": [vp],
+    "dg_comm_init": [ctypes.c_int, ctypes.c_int, vp],
+    "dg_comm_finalize": [],
+    "dg_host_shard_locate": [u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, u64, ctypes.POINTER(ctypes.c_int64)],
     "dg_host_prng_vector": [vp, u64, vp],
     "dg_host_query_positions": [vp, u64, u32, u32, vp],
     "dg_host_blake3": [vp, ctypes.c_size_t, vp],
@@ -101,6 +105,21 @@ def device_info():
     mem = ctypes.c_size_t(0)
     check(lib().dg_device_info(name, 128, ctypes.byref(sms), ctypes.byref(mem)))
     return {"name": name.value.decode(), "sm_count": sms.value, "total_mem": mem.value}
+
+
+def comm_init_from_torch(dist, device_index):
+    """Joins the NCCL communicator used to shard one proof over the ranks of an initialised torch.distributed group."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ident = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device_index}")
+    if rank == 0:
+        buf = ctypes.create_string_buffer(128)
+        check(lib().dg_comm_unique_id(buf))
+        ident.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+    dist.broadcast(ident, src=0)
+    raw = bytes(ident.cpu().numpy().tobytes())
+    check(lib().dg_comm_init(rank, world, raw))
+    return rank, world
 
 
 class DeviceBuffer:

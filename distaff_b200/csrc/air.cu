@@ -79,17 +79,17 @@ struct Acc {
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const AirParams P) {
     const unsigned long long n = 1ULL << P.log_n;
-    const unsigned long long E = n << 3;
     const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= E) return;
-    const unsigned long long c8 = gid >> P.log_n, k = gid & (n - 1);
+    if (gid >= n * (unsigned long long)P.num_c8) return;
+    const unsigned long long c8_local = gid >> P.log_n, k = gid & (n - 1);
+    const unsigned long long c8 = c8_local + P.c8_base;
     const unsigned long long s = (k << 3) + c8;                       // evaluation-domain step
     const int stride = 1 << (P.log_blowup - 3);
-    const unsigned long long coset = c8 * stride;
-    const unsigned long long N = n << P.log_blowup;
-    const unsigned long long lde_index = s * (unsigned long long)stride;   // = k*blowup + coset
-    const fe *cur_p = P.ext + coset * n + k;
-    const fe *nxt_p = P.ext + coset * n + ((k + 1) & (n - 1));
+    const unsigned long long N = P.col_stride;                         // column stride of the local slab
+    const unsigned long long lde_index = s * (unsigned long long)stride;   // = k*blowup + c8*stride
+    const fe *cur_p = P.ext + (c8_local * stride) * n + k;            // the slab starts at coset c8_base*stride
+    const fe *nxt_p = P.ext + (c8_local * stride) * n + ((k + 1) & (n - 1));
+    const unsigned long long out_idx = (c8_local << P.log_n) + k;
 
     const int cl = P.cl, ll = P.ll, sl = P.sl;
     const int ctx_off = 15, loop_off = 15 + P.ctx_depth, stk_off = 15 + P.ctx_depth + P.loop_depth;
@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         fe xp = tw_pow(P.twN, lde_index * P.b_adj);                  // x^(6n+2), x = w_N^lde_index
         fe i_res = fe_add(fe_sub(biA, P.KiA), fe_mul(fe_sub(biB, P.KiB), xp));
         fe f_res = fe_add(fe_sub(bfA, P.KfA), fe_mul(fe_sub(bfB, P.KfB), xp));
-        P.i_ev[s] = i_res;
-        P.f_ev[s] = f_res;
+        P.i_ev[out_idx] = i_res;
+        P.f_ev[out_idx] = f_res;
     }
 
     // ---- op flags (trace_state.rs:281-350) ----------------------------------------------------------------------------------
@@ -468,12 +468,12 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         if (acc.nonzero) atomicExch(P.violation, (unsigned)(k + 1));
         t_res = ZERO;
     }
-    P.t_ev[s] = t_res;
+    P.t_ev[out_idx] = t_res;
 }
 
 void launch_constraint_eval(Context &c, const AirParams &P) {
     air_upload_constants();
-    const unsigned long long E = 8ULL << P.log_n;
+    const unsigned long long E = (unsigned long long)P.num_c8 << P.log_n;
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("DG_AIR_LB"); variant = e ? atoi(e) : 4; }   // 4 blocks/SM (128 registers, some local spills) measured fastest on B200
     const unsigned grid = (unsigned)((E + 127) / 128);

@@ -9,8 +9,10 @@ struct AirParams {
     int cl, ll, sl;                     // padded stack lengths: max(depth, 1 / 1 / 8)   (trace_state.rs:58-60)
     int log_n, log_blowup;
     int n_boundary_regs;                // registers [0, n_boundary_regs) carry boundary coefficients
-    const fe *ext;                      // extended trace, [w][N] coset-major
-    fe *i_ev, *f_ev, *t_ev;             // outputs over the 8n-point evaluation domain, natural order
+    const fe *ext;                      // extended trace slab of this rank: [w][local cosets][n], column stride col_stride
+    unsigned long long col_stride;
+    int c8_base, num_c8;                // evaluation-domain cosets handled here: c8 in [c8_base, c8_base + num_c8)  (c8 = step mod 8)
+    fe *i_ev, *f_ev, *t_ev;             // outputs, coset-major: [c8 - c8_base][k]  (step s = 8k + c8)
     const fe *periodic;                 // [128][23] = sponge ARK (8) | masks (3) | hasher ARK (12), row = step % 128
     const fe *coefA, *coefB;            // per transition constraint (evaluation order): cc[2i], cc[2i+1] of its flattened slot
     const fe *bAi, *bBi, *bAf, *bBf;    // per register boundary coefficients (first step / last step)

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "prover.h"
 #include "host_fs.h"
+#include "shard.h"
 
 namespace dg {
 void hash_trace_rows(Context &c, const fe *ext, void *leaves, int w, int log_n, int log_blowup);
@@ -300,6 +301,20 @@ int dg_proof_pow_nonce(const dg_proof_t *proof, uint64_t *nonce) {
     return guarded([&] { DG_REQUIRE(proof && nonce, "null argument"); *nonce = ((const Proof *)proof)->pow_nonce; });
 }
 void dg_proof_free(dg_proof_t *proof) { delete (Proof *)proof; }
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------------------------------------
+int dg_comm_unique_id(uint8_t id128[128]) { return guarded([&] { comm_unique_id(id128); }); }
+int dg_comm_init(int rank, int world, const uint8_t id128[128]) {
+    return guarded([&] { Context &c = ctx(); std::lock_guard<std::mutex> lk(c.mu); comm_init(c, rank, world, id128); });
+}
+int dg_comm_finalize(void) { return guarded([&] { Context &c = ctx(); std::lock_guard<std::mutex> lk(c.mu); comm_finalize(c); }); }
+int dg_host_shard_locate(uint64_t n, int log_blk, int log_g, int is_node, uint64_t index, int64_t out[3]) {
+    return guarded([&] {
+        ShardGeom geo; geo.n = n; geo.log_blk = log_blk; geo.log_g = log_g;
+        ShardLocation l = is_node ? geo.node(index) : geo.item(index);
+        out[0] = l.owner; out[1] = l.upper ? 1 : 0; out[2] = (int64_t)l.index;
+    });
+}
 
 // ---- host-only helpers (no device access) ---------------------------------------------------------------------------------------------
 int dg_host_prng_vector(const uint8_t seed[32], uint64_t count, uint8_t *out16) {

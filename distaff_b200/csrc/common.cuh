@@ -80,6 +80,7 @@ struct Context {
     DevBuf ntt_tmp;                         // scratch of the multi-pass transforms
     std::string last_error;
     unsigned long long launches = 0;        // kernels launched by this library (bench.py's gpu_launches)
+    int rank = 0, world = 1;                // multi-GPU sharding (comm.cu); world == 1: no communication
 
     TwiddleRef twiddle(int log_order, bool inverse);
     std::map<int, DevBuf> single_tables;    // full power tables w^e, e < 2^log_order (small orders only)
@@ -104,6 +105,14 @@ void ntt_batch(Context &c, const fe *src, fe *dst, int log_n, int batch, size_t 
 // coset low-degree extension: coefficient vectors (batch of them, `coeff_len` = fold * n coefficients each, stride
 // `src_stride`) are evaluated over the 2^log_blowup cosets of the order-n subgroup; output per vector is
 // [coset c][k] = P(w_N^c * w_n^k), N = n << log_blowup, i.e. LDE index i = (k << log_blowup) + c lives at c*n + k.
-void lde_batch(Context &c, const fe *src, fe *dst, int log_n, int log_blowup, int fold, int batch, size_t src_stride, size_t dst_stride);
+void lde_batch(Context &c, const fe *src, fe *dst, int log_n, int log_blowup, int fold, int batch, size_t src_stride, size_t dst_stride,
+               unsigned coset0 = 0, unsigned ncosets = 0 /* 0 = all 2^log_blowup */);
+
+// ---- multi-GPU plumbing (comm.cu) -----------------------------------------------------------------------------------------
+void comm_unique_id(uint8_t out[128]);
+void comm_init(Context &c, int rank, int world, const uint8_t id_bytes[128]);
+void comm_finalize(Context &c);
+void comm_all_gather(Context &c, const void *send, void *recv, size_t bytes_per_rank);
+void comm_all_reduce_max_u32(Context &c, unsigned *buf, size_t count);
 
 }  // namespace dg

@@ -38,6 +38,7 @@ struct PassGeom {
     const fe *cw_point;                 // cw_point[e] = (w_N^in_point)^e, e < cw_point_mask + 1
     unsigned cw_point_mask;
     int log_blowup;
+    unsigned coset0;                    // first coset handled by this launch (blockIdx.y = coset - coset0)
     const fe *roots;                    // per-stage twiddle tables of the L-point transform: W_st[j] = w_L^(j << st), back to back
 };
 
@@ -121,9 +122,9 @@ __device__ __forceinline__ void ntt_round(const fe *__restrict__ src, fe *__rest
                 const long long j = in_base + (long long)t * g.in_lane + (long long)pos * g.in_point;
                 if (g.coset_fast) {
                     // p[j] * w_N^(c*pos*in_point); the lane part w_N^(c*lane) rides on the output twiddle
-                    x[m] = fe_mul(src[j], g.cw_point[((unsigned)blockIdx.y * (unsigned)pos) & g.cw_point_mask]);
+                    x[m] = fe_mul(src[j], g.cw_point[((g.coset0 + (unsigned)blockIdx.y) * (unsigned)pos) & g.cw_point_mask]);
                 } else if (g.coset_on) {
-                    const unsigned long long c = blockIdx.y;
+                    const unsigned long long c = g.coset0 + blockIdx.y;
                     fe v = fe_make(0, 0);
                     for (int f = 0; f < g.fold; f++) {
                         const long long jj = j + (long long)f * g.fold_stride;
@@ -144,7 +145,7 @@ __device__ __forceinline__ void ntt_round(const fe *__restrict__ src, fe *__rest
             if (LAST) {                        // position q holds X[bitrev(q)]
                 const unsigned k = __brev((unsigned)pos) >> (32 - LOG_L);
                 fe v = x[m];
-                if (g.coset_fast && g.tw_on) v = fe_mul(v, tw_lookup(g.cw, (unsigned long long)(tile * T + t) * (((unsigned long long)k << g.log_blowup) + blockIdx.y)));
+                if (g.coset_fast && g.tw_on) v = fe_mul(v, tw_lookup(g.cw, (unsigned long long)(tile * T + t) * (((unsigned long long)k << g.log_blowup) + g.coset0 + blockIdx.y)));
                 else if (g.tw_on) v = fe_mul(v, tw_lookup(g.tw, (unsigned long long)(tile * T + t) * k));
                 if (g.has_scale) v = fe_mul(v, g.scale);
                 dst[(long long)t * g.out_lane + (long long)k * g.out_point] = v;
@@ -226,7 +227,7 @@ static int split_passes(int log_n, int l[3]) {
     return 3;
 }
 
-struct CosetSpec { bool on; int log_blowup; int fold; };
+struct CosetSpec { bool on; int log_blowup; int fold; unsigned coset0; };
 
 // Runs the passes of one batched transform.  `by` = number of y-batches (cosets for the LDE, else 1), `bz` = vectors.
 // src strides: vector stride src_stride (z), y stride 0 for the LDE (every coset reads the same coefficients).
@@ -246,6 +247,7 @@ static void run_transform(Context &c, const fe *src, fe *dst, int log_n, bool in
         base.fold_stride = n;
         base.cw = c.twiddle(log_n + cs.log_blowup, false);
         base.log_blowup = cs.log_blowup;
+        base.coset0 = cs.coset0;
         if (cs.fold == 1) {
             // order of w_N^in_point where in_point = n / N1 (first pass) : N / in_point = N1 << log_blowup
             const int log_order = l[0] + cs.log_blowup;
@@ -327,20 +329,22 @@ void ntt_batch(Context &c, const fe *src, fe *dst, int log_n, int batch, size_t 
     for (size_t b0 = 0; b0 < (size_t)batch; b0 += max_chunk) {
         size_t nb = std::min(max_chunk, (size_t)batch - b0);
         run_transform(c, src + b0 * src_stride, dst + b0 * dst_stride, log_n, inverse, 1, (unsigned)nb, (long long)src_stride, 0,
-                      (long long)dst_stride, CosetSpec{false, 0, 1});
+                      (long long)dst_stride, CosetSpec{false, 0, 1, 0});
     }
 }
 
-void lde_batch(Context &c, const fe *src, fe *dst, int log_n, int log_blowup, int fold, int batch, size_t src_stride, size_t dst_stride) {
+void lde_batch(Context &c, const fe *src, fe *dst, int log_n, int log_blowup, int fold, int batch, size_t src_stride, size_t dst_stride,
+               unsigned coset0, unsigned ncosets) {
     DG_REQUIRE(log_n >= 1 && log_n + log_blowup <= 30, "LDE domain too large");
     const size_t n = (size_t)1 << log_n;
-    const unsigned cosets = 1u << log_blowup;
+    const unsigned cosets = ncosets ? ncosets : (1u << log_blowup);
+    DG_REQUIRE(coset0 + cosets <= (1u << log_blowup), "coset range out of bounds");
     size_t max_chunk = std::max<size_t>(1, ((size_t)1 << 30) / (n * cosets * sizeof(fe)));
     if (max_chunk > 65535) max_chunk = 65535;
     for (size_t b0 = 0; b0 < (size_t)batch; b0 += max_chunk) {
         size_t nb = std::min(max_chunk, (size_t)batch - b0);
         run_transform(c, src + b0 * src_stride, dst + b0 * dst_stride, log_n, false, cosets, (unsigned)nb, (long long)src_stride,
-                      (long long)n, (long long)dst_stride, CosetSpec{true, log_blowup, fold});
+                      (long long)n, (long long)dst_stride, CosetSpec{true, log_blowup, fold, coset0});
     }
 }
 

@@ -255,19 +255,16 @@ void compose(Context &c, const fe *t1q, const fe *t2q, const fe *cq, fe *comp, u
 }
 
 // ---- gathers for the query openings -----------------------------------------------------------------------------------------------------------
-// out[q*w + j] = ext[j][phys(position_q)]   (coset-major extended trace)
-__global__ void gather_rows_kernel(const fe *__restrict__ ext, int w, int log_n, int log_blowup, const unsigned long long *__restrict__ positions,
+// out[q*w + j] = ext[j * col_stride + phys_q]   (phys_q = position inside the rank's coset-major slab, computed on the host)
+__global__ void gather_rows_kernel(const fe *__restrict__ ext, int w, unsigned long long col_stride, const unsigned long long *__restrict__ phys,
                                    int nq, fe *__restrict__ out) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nq * w) return;
     int q = t / w, j = t % w;
-    unsigned long long i = positions[q];
-    unsigned long long c = i & ((1ULL << log_blowup) - 1ULL), k = i >> log_blowup;
-    unsigned long long N = 1ULL << (log_n + log_blowup);
-    out[t] = ext[(unsigned long long)j * N + (c << log_n) + k];
+    out[t] = ext[(unsigned long long)j * col_stride + phys[q]];
 }
-void gather_rows(Context &c, const fe *ext, int w, int log_n, int log_blowup, const unsigned long long *d_positions, int nq, fe *d_out) {
-    gather_rows_kernel<<<(nq * w + 127) / 128, 128, 0, c.stream>>>(ext, w, log_n, log_blowup, d_positions, nq, d_out); c.launches++;
+void gather_rows(Context &c, const fe *ext, int w, unsigned long long col_stride, const unsigned long long *d_phys, int nq, fe *d_out) {
+    gather_rows_kernel<<<(nq * w + 127) / 128, 128, 0, c.stream>>>(ext, w, col_stride, d_phys, nq, d_out); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 // out[t] = src[idx[t]] for 32-byte items

@@ -6,6 +6,7 @@
 #include "air.h"
 #include "host_fs.h"
 #include "poly.h"
+#include "shard.h"
 #include <array>
 #include <memory>
 
@@ -53,7 +54,6 @@ void debug_dump_host(const char *name, const void *host, size_t bytes) {
     fclose(f);
 }
 
-typedef std::array<uint8_t, 32> Digest;
 
 // fetches 32-byte items src[idx[i]] to the host
 std::vector<Digest> fetch32(Context &c, const void *src, const std::vector<uint64_t> &idx) {
@@ -75,13 +75,13 @@ std::vector<fe> fetch16(Context &c, const fe *src, const std::vector<uint64_t> &
     return out;
 }
 
-// materialises the node lists of a batch proof; `leaf_fetch` maps leaf indices to 32-byte leaves
-template <typename LeafFetch>
-std::vector<std::vector<Digest>> resolve_plan(Context &c, const fs::BatchPlan &plan, const void *d_nodes, LeafFetch leaf_fetch) {
+// materialises the node lists of a batch proof; `leaf_fetch` maps leaf indices and `node_fetch` heap indices to 32-byte values
+template <typename LeafFetch, typename NodeFetch>
+std::vector<std::vector<Digest>> resolve_plan(const fs::BatchPlan &plan, LeafFetch leaf_fetch, NodeFetch node_fetch) {
     std::vector<uint64_t> leaf_idx, node_idx;
     for (auto &slot : plan.nodes)
         for (auto &r : slot) (r.leaf ? leaf_idx : node_idx).push_back(r.index);
-    std::vector<Digest> leaves = leaf_fetch(leaf_idx), nodes = fetch32(c, d_nodes, node_idx);
+    std::vector<Digest> leaves = leaf_fetch(leaf_idx), nodes = node_fetch(node_idx);
     std::vector<std::vector<Digest>> out(plan.nodes.size());
     size_t li = 0, ni = 0;
     for (size_t s = 0; s < plan.nodes.size(); s++)
@@ -142,18 +142,28 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
     Proof *proof = new Proof();
     std::unique_ptr<Proof> guard(proof);
 
+    // ---- sharding: rank g owns the LDE cosets [c0, c0 + nc) of every column (world == 1: all of them) ------------------------------
+    const int G = c.world, g = c.rank;
+    int log_g = 0;
+    while ((1 << log_g) < G) log_g++;
+    DG_REQUIRE((b >> log_g) >= 4 && G <= 8, "extension factor too small for this many GPUs (need >= 4 cosets per rank)");
+    const int log_nc = log_b - log_g;
+    const uint64_t nc = 1ULL << log_nc, N_loc = n * nc;
+    const unsigned c0 = (unsigned)(g * nc);
+
     // ---- 1: extend execution trace ---------------------------------------------------------------------------------------------------
     clk.mark(0);
-    DevBuf polys((size_t)w * n * 16), ext((size_t)w * N * 16);
+    DevBuf polys((size_t)w * n * 16), ext((size_t)w * N_loc * 16);
     ntt_batch(c, d_regs, polys.as<fe>(), log_n, w, n, n, true);
-    lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N);
+    lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
 
     // ---- 2: trace Merkle tree ----------------------------------------------------------------------------------------------------------
     clk.mark(1);
-    DevBuf t_leaves(N * 32), t_nodes(N * 32);
-    hash_trace_rows(c, ext.as<fe>(), t_leaves.p, w, log_n, log_b);
-    merkle_build(c, t_leaves.p, t_nodes.p, N);
-    d2h(c, proof->trace_root, (const uint8_t *)t_nodes.p + 32, 32);
+    DevBuf t_leaves(N_loc * 32);
+    hash_trace_rows(c, ext.as<fe>(), t_leaves.p, w, log_n, log_nc);          // local rows, [k][c - c0]
+    ShardedTree t_tree;
+    t_tree.build(c, t_leaves.p, n, log_nc);
+    memcpy(proof->trace_root, t_tree.root.data(), 32);
 
     // ---- 3: evaluate constraints --------------------------------------------------------------------------------------------------------
     clk.mark(2);
@@ -185,13 +195,17 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
     DG_CUDA(cudaMemsetAsync(d_violation.p, 0, 4, c.stream));
     DevBuf evals(3 * E * 16);
     {
+        const int num_c8 = 8 >> log_g;
+        const uint64_t E_loc = n * num_c8;
+        DevBuf evals_loc(3 * E_loc * 16), gathered(3 * E * 16);
         AirParams P;
         memset(&P, 0, sizeof P);
         P.w = w; P.ctx_depth = ctx_depth; P.loop_depth = loop_depth; P.stack_depth = stack_depth;
         P.cl = std::max<int>(ctx_depth, 1); P.ll = std::max<int>(loop_depth, 1); P.sl = std::max(stack_depth, 8);
         P.log_n = log_n; P.log_blowup = log_b; P.n_boundary_regs = cc.n_boundary_regs;
-        P.ext = ext.as<fe>();
-        P.i_ev = evals.as<fe>(); P.f_ev = evals.as<fe>() + E; P.t_ev = evals.as<fe>() + 2 * E;
+        P.ext = ext.as<fe>(); P.col_stride = N_loc;
+        P.c8_base = g * num_c8; P.num_c8 = num_c8;
+        P.i_ev = evals_loc.as<fe>(); P.f_ev = evals_loc.as<fe>() + E_loc; P.t_ev = evals_loc.as<fe>() + 2 * E_loc;
         P.periodic = d_periodic.as<fe>();
         const fe *base = d_coef.as<fe>();
         P.coefA = base; P.coefB = base + T;
@@ -200,12 +214,17 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
         P.twN = c.twiddle(log_N, false);
         P.b_adj = 6 * n + 2;
         static const int GROUP_DEG[6] = {2, 3, 4, 6, 7, 8};
-        for (int g = 0; g < 6; g++) P.inc[g] = (8 * n - 1) - (n - 1) * GROUP_DEG[g];
+        for (int gi = 0; gi < 6; gi++) P.inc[gi] = (8 * n - 1) - (n - 1) * GROUP_DEG[gi];
         P.violation = d_violation.as<unsigned>();
         launch_constraint_eval(c, P);
+        comm_all_reduce_max_u32(c, d_violation.as<unsigned>(), 1);
         unsigned violation = 0;
         d2h(c, &violation, d_violation.p, 4);
         if (violation) throw Error(DG_ERR_UNSATISFIED, "transition constraints at step " + std::to_string(violation - 1) + " were not satisfied");
+        // every rank needs all three accumulators to interpolate them: gather the coset slabs, then go to natural step order
+        for (int v = 0; v < 3; v++)
+            comm_all_gather(c, evals_loc.as<fe>() + v * E_loc, gathered.as<fe>() + v * E, E_loc * 16);
+        transpose_cosets(c, gathered.as<fe>(), evals.as<fe>(), log_n, 3, 3);
     }
     debug_dump(c, "i_evals", evals.as<fe>(), E * 16);
     debug_dump(c, "f_evals", evals.as<fe>() + E, E * 16);
@@ -229,11 +248,12 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
 
     // ---- 5: constraint evaluations over the LDE domain + their Merkle tree -----------------------------------------------------------------
     clk.mark(4);
-    DevBuf c_ext(N * 16), c_nodes(N / 2 * 32);
-    lde_batch(c, combined.as<fe>(), c_ext.as<fe>(), log_n, log_b, 8, 1, E, N);
-    constraint_tree_first_level(c, c_ext.as<fe>(), log_n, log_b, c_nodes.p);
-    merkle_finish(c, c_nodes.p, N / 4);
-    d2h(c, proof->constraint_root, (const uint8_t *)c_nodes.p + 32, 32);
+    DevBuf c_ext(N_loc * 16), c_items((N_loc / 4) * 32);
+    lde_batch(c, combined.as<fe>(), c_ext.as<fe>(), log_n, log_b, 8, 1, E, N_loc, c0, (unsigned)nc);
+    constraint_items_local(c, c_ext.as<fe>(), log_n, log_nc, c_items.p);      // first tree level: H(4 evaluations), [k][c4 local]
+    ShardedTree c_tree;
+    c_tree.build(c, c_items.p, n, log_nc - 2);
+    memcpy(proof->constraint_root, c_tree.root.data(), 32);
 
     // ---- 6: DEEP composition polynomial ---------------------------------------------------------------------------------------------------------
     clk.mark(5);
@@ -266,7 +286,13 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
         syn_div(c, combined.as<fe>(), scratch2.as<fe>(), scratch.as<fe>(), E, z_t.ref(), zi_t.ref(), c_at_z);   // (C(x) - C(z)) / (x - z)
         compose(c, t1, t2, scratch2.as<fe>(), comp.as<fe>(), n, E, 6 * n + 1, dc.t1_degree, dc.t2_degree, dc.constraints);
         debug_dump(c, "composition_poly", comp.p, E * 16);
-        lde_batch(c, comp.as<fe>(), comp_ext.as<fe>(), log_n, log_b, 8, 1, E, N);
+        if (G == 1) {
+            lde_batch(c, comp.as<fe>(), comp_ext.as<fe>(), log_n, log_b, 8, 1, E, N);
+        } else {   // extend the own cosets, then every rank gets the whole vector (rank-major == coset-major) to run FRI redundantly
+            DevBuf comp_loc(N_loc * 16);
+            lde_batch(c, comp.as<fe>(), comp_loc.as<fe>(), log_n, log_b, 8, 1, E, N_loc, c0, (unsigned)nc);
+            comm_all_gather(c, comp_loc.p, comp_ext.p, N_loc * 16);
+        }
     }
 
     // ---- 7: FRI layers ---------------------------------------------------------------------------------------------------------------------------
@@ -321,32 +347,66 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
     fs::ByteWriter out;
     {
         const int nq = (int)positions.size();
-        // trace rows at the queried positions (trace_table.rs:127-134)
+        // trace rows at the queried positions (trace_table.rs:127-134): the rank owning the position's coset reads the row
         std::vector<fe> rows((size_t)nq * w);
         {
+            std::vector<uint64_t> phys(nq);
+            std::vector<int> owners(nq);
+            for (int q = 0; q < nq; q++) {
+                const uint64_t cpos = positions[q] & (b - 1), k = positions[q] >> log_b;
+                owners[q] = (int)(cpos >> log_nc);
+                phys[q] = owners[q] == g ? (((cpos - c0) << log_n) + k) : 0;
+            }
             DevBuf d_pos(nq * 8), d_rows((size_t)nq * w * 16);
-            h2d(c, d_pos.p, positions.data(), nq * 8);
-            gather_rows(c, ext.as<fe>(), w, log_n, log_b, d_pos.as<unsigned long long>(), nq, d_rows.as<fe>());
-            d2h(c, rows.data(), d_rows.p, rows.size() * 16);
+            h2d(c, d_pos.p, phys.data(), nq * 8);
+            gather_rows(c, ext.as<fe>(), w, N_loc, d_pos.as<unsigned long long>(), nq, d_rows.as<fe>());
+            std::vector<uint8_t> got = exchange_owned(c, d_rows.p, nq, (size_t)w * 16, owners);
+            memcpy(rows.data(), got.data(), got.size());
         }
         // trace tree openings: leaves are the row hashes
         fs::BatchPlan tplan = fs::plan_batch_proof(positions, N);
-        auto trace_nodes = resolve_plan(c, tplan, t_nodes.p, [&](const std::vector<uint64_t> &idx) { return fetch32(c, t_leaves.p, idx); });
+        auto trace_nodes = resolve_plan(tplan, [&](const std::vector<uint64_t> &idx) { return t_tree.fetch_items(c, idx); },
+                                        [&](const std::vector<uint64_t> &idx) { return t_tree.fetch_nodes(c, idx); });
 
         // constraint tree openings: leaf j = evaluations (2j, 2j+1), unhashed (prover.rs:180-187)
-        const Layout c_lay{log_N, log_b};
         auto constraint_leaves = [&](const std::vector<uint64_t> &idx) {
             std::vector<uint64_t> phys;
-            for (uint64_t j : idx) { phys.push_back(c_lay.phys(2 * j)); phys.push_back(c_lay.phys(2 * j + 1)); }
-            std::vector<fe> v = fetch16(c, c_ext.as<fe>(), phys);
+            std::vector<int> owners;
+            for (uint64_t j : idx) {
+                const uint64_t i = 2 * j, cpos = i & (b - 1), k = i >> log_b;
+                const int owner = (int)(cpos >> log_nc);
+                owners.push_back(owner);
+                const uint64_t p0 = owner == g ? (((cpos - c0) << log_n) + k) : 0;
+                phys.push_back(p0);
+                phys.push_back(owner == g ? p0 + n : 0);            // evaluation 2j+1 lives in the next coset, same k
+            }
             std::vector<Digest> o(idx.size());
-            for (size_t i = 0; i < idx.size(); i++) memcpy(o[i].data(), &v[2 * i], 32);
+            if (idx.empty()) return o;
+            DevBuf d_idx(phys.size() * 8), d_out(phys.size() * 16);
+            h2d(c, d_idx.p, phys.data(), phys.size() * 8);
+            gather16(c, c_ext.as<fe>(), d_idx.as<unsigned long long>(), (int)phys.size(), d_out.as<fe>());
+            std::vector<uint8_t> got = exchange_owned(c, d_out.p, idx.size(), 32, owners);
+            memcpy(o.data(), got.data(), got.size());
+            return o;
+        };
+        auto constraint_nodes = [&](const std::vector<uint64_t> &idx) {
+            // heap indices of the tree over N/2 leaves: [N/4, N/2) is the first hashed level (= level-0 items of c_tree)
+            std::vector<uint64_t> items, inner;
+            std::vector<size_t> ipos, npos;
+            for (size_t q = 0; q < idx.size(); q++) {
+                if (idx[q] >= N / 4) { items.push_back(idx[q] - N / 4); ipos.push_back(q); }
+                else { inner.push_back(idx[q]); npos.push_back(q); }
+            }
+            std::vector<Digest> o(idx.size());
+            std::vector<Digest> a = c_tree.fetch_items(c, items), bb = c_tree.fetch_nodes(c, inner);
+            for (size_t i = 0; i < a.size(); i++) o[ipos[i]] = a[i];
+            for (size_t i = 0; i < bb.size(); i++) o[npos[i]] = bb[i];
             return o;
         };
         std::vector<uint64_t> c_positions = fs::constraint_positions(positions);
         fs::BatchPlan cplan = fs::plan_batch_proof(c_positions, N / 2);
         std::vector<Digest> c_values = constraint_leaves(cplan.value_leaves);
-        auto c_nodes_open = resolve_plan(c, cplan, c_nodes.p, constraint_leaves);
+        auto c_nodes_open = resolve_plan(cplan, constraint_leaves, constraint_nodes);
 
         // ---- serialise (proof.rs:10-37; bincode: u64 length prefixes, arrays raw, little endian)
         out.raw(proof->trace_root, 32);
@@ -377,7 +437,8 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
             for (uint64_t p : fpos)
                 for (int j = 0; j < 4; j++) phys.push_back(L.layout.phys(p + j * R));
             std::vector<fe> vals = fetch16(c, L.vals, phys);
-            auto nodes = resolve_plan(c, plan, L.nodes.p, [&](const std::vector<uint64_t> &idx) { return fetch32(c, L.leaves.p, idx); });
+            auto nodes = resolve_plan(plan, [&](const std::vector<uint64_t> &idx) { return fetch32(c, L.leaves.p, idx); },
+                                      [&](const std::vector<uint64_t> &idx) { return fetch32(c, L.nodes.p, idx); });
             out.raw(L.root.data(), 32);
             out.u64(fpos.size());
             for (auto &v : vals) out.felt(v);

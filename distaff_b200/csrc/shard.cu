@@ -1,0 +1,200 @@
+#include "shard.h"
+#include "blake3.cuh"
+#include "poly.h"
+
+namespace dg {
+
+// ---- index algebra (host) ---------------------------------------------------------------------------------------------------
+ShardLocation ShardGeom::item(uint64_t i) const {
+    const uint64_t blk = 1ULL << log_blk, per_k = blk << log_g;
+    const uint64_t k = i / per_k, within = i % per_k;
+    ShardLocation r;
+    r.owner = (int)(within >> log_blk);
+    r.upper = false;
+    r.index = (k << log_blk) + (within & (blk - 1));
+    return r;
+}
+ShardLocation ShardGeom::node(uint64_t h) const {
+    const uint64_t upper_nodes = n << log_g;              // the replicated tree holds heap indices [1, 2 * n * G)
+    ShardLocation r;
+    if (h < 2 * upper_nodes) { r.owner = -1; r.upper = true; r.index = h; return r; }
+    int lvl = 63 - __builtin_clzll(h);
+    const uint64_t S = 1ULL << lvl, o = h - S;
+    const uint64_t span = items() / S;                    // level-0 items below this node (< blk)
+    const uint64_t i0 = o * span;
+    ShardLocation it = item(i0);
+    const uint64_t local_level = (n << log_blk) / span;   // size of the local level with the same span
+    r.owner = it.owner;
+    r.upper = false;
+    r.index = local_level + it.index / span;
+    return r;
+}
+
+// ---- kernels ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hash_pairs_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, unsigned long long count) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t m[16], cv[8];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint4 v = in[4 * i + q];
+        m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+    }
+    b3::hash64(m, cv);
+    out[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    out[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+// levels of a heap-layout tree from L/2 nodes down to (and including) the level with `stop` nodes
+void merkle_build_partial(Context &c, const void *leaves, void *nodes, unsigned long long L, unsigned long long stop) {
+    uint4 *nd = (uint4 *)nodes;
+    const uint4 *in = (const uint4 *)leaves;
+    for (unsigned long long m = L / 2; m >= stop && m >= 1; m >>= 1) {
+        hash_pairs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(in, nd + 2 * m, m); c.launches++;
+        DG_CUDA(cudaGetLastError());
+        in = nd + 2 * m;
+    }
+}
+
+// upper[(n << log_g) + (k << log_g) + g] = gathered[g][k]
+__global__ void interleave_roots_kernel(const uint4 *__restrict__ gathered, uint4 *__restrict__ upper, unsigned long long n, int log_g) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (n << log_g)) return;
+    const unsigned long long g = t / n, k = t % n;
+    const unsigned long long dst = (n << log_g) + (k << log_g) + g;
+    upper[2 * dst] = gathered[2 * t];
+    upper[2 * dst + 1] = gathered[2 * t + 1];
+}
+void interleave_roots(Context &c, const void *gathered, void *upper, unsigned long long n, int log_g) {
+    const unsigned long long total = n << log_g;
+    interleave_roots_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>((const uint4 *)gathered, (uint4 *)upper, n, log_g); c.launches++;
+    DG_CUDA(cudaGetLastError());
+}
+
+// out[b][k][c] = in[b][c][k]
+__global__ void transpose_cosets_kernel(const fe *__restrict__ in, fe *__restrict__ out, int log_n, int log_c) {
+    const unsigned long long n = 1ULL << log_n;
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int C = 1 << log_c;
+    const fe *src = in + ((unsigned long long)blockIdx.y << (log_n + log_c));
+    fe *dst = out + ((unsigned long long)blockIdx.y << (log_n + log_c)) + (k << log_c);
+    for (int cc = 0; cc < C; cc++) dst[cc] = src[(unsigned long long)cc * n + k];
+}
+void transpose_cosets(Context &c, const fe *in, fe *out, int log_n, int log_c, int batch) {
+    const unsigned long long n = 1ULL << log_n;
+    transpose_cosets_kernel<<<dim3((unsigned)((n + 127) / 128), batch), 128, 0, c.stream>>>(in, out, log_n, log_c); c.launches++;
+    DG_CUDA(cudaGetLastError());
+}
+
+// items[k * (nc/4) + c4] = H(ev[4c4][k], ev[4c4+1][k], ev[4c4+2][k], ev[4c4+3][k]) over the local cosets (prover.rs:84-86,180-187)
+__global__ void __launch_bounds__(256) constraint_items_kernel(const fe *__restrict__ ev, int log_n, int log_nc, uint4 *__restrict__ items) {
+    const unsigned long long n = 1ULL << log_n;
+    const unsigned long long total = n << (log_nc - 2);
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const unsigned long long c4 = t >> log_n, k = t & (n - 1);
+    const unsigned long long j = (k << (log_nc - 2)) + c4;
+    uint32_t m[16], cv[8];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const uint4 x = reinterpret_cast<const uint4 *>(ev)[(4 * c4 + u) * n + k];
+        m[4 * u] = x.x; m[4 * u + 1] = x.y; m[4 * u + 2] = x.z; m[4 * u + 3] = x.w;
+    }
+    b3::hash64(m, cv);
+    items[2 * j] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    items[2 * j + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+void constraint_items_local(Context &c, const fe *evals_local, int log_n, int log_nc, void *items) {
+    const unsigned long long total = (1ULL << log_n) << (log_nc - 2);
+    constraint_items_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(evals_local, log_n, log_nc, (uint4 *)items); c.launches++;
+    DG_CUDA(cudaGetLastError());
+}
+
+// ---- sharded tree -------------------------------------------------------------------------------------------------------------------
+void ShardedTree::build(Context &c, const void *items_local_dev, uint64_t n, int log_blk) {
+    int log_g = 0;
+    while ((1 << log_g) < c.world) log_g++;
+    geom.n = n; geom.log_blk = log_blk; geom.log_g = log_g;
+    items_local = items_local_dev;
+    const uint64_t local_items = n << log_blk;
+    const void *roots = items_local_dev;
+    if (log_blk > 0) {
+        local_nodes.alloc(local_items * 32);
+        merkle_build_partial(c, items_local_dev, local_nodes.p, local_items, n);
+        roots = (const uint8_t *)local_nodes.p + n * 32;           // heap level with n nodes
+    }
+    const uint64_t upper_level = n << log_g;
+    upper.alloc(2 * upper_level * 32);
+    DevBuf gathered(upper_level * 32);
+    comm_all_gather(c, roots, gathered.p, n * 32);
+    interleave_roots(c, gathered.p, upper.p, n, log_g);
+    merkle_finish(c, upper.p, upper_level);
+    DG_CUDA(cudaMemcpyAsync(root.data(), (const uint8_t *)upper.p + 32, 32, cudaMemcpyDeviceToHost, c.stream));
+    DG_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+std::vector<uint8_t> exchange_owned(Context &c, const void *d_local, size_t count, size_t item_bytes, const std::vector<int> &owners) {
+    std::vector<uint8_t> out(count * item_bytes);
+    if (count == 0) return out;
+    const size_t bytes = count * item_bytes;
+    DevBuf all(bytes * c.world);
+    comm_all_gather(c, d_local, all.p, bytes);
+    std::vector<uint8_t> host(bytes * c.world);
+    DG_CUDA(cudaMemcpyAsync(host.data(), all.p, host.size(), cudaMemcpyDeviceToHost, c.stream));
+    DG_CUDA(cudaStreamSynchronize(c.stream));
+    for (size_t q = 0; q < count; q++) {
+        const int o = owners[q] < 0 ? c.rank : owners[q];
+        memcpy(out.data() + q * item_bytes, host.data() + (size_t)o * bytes + q * item_bytes, item_bytes);
+    }
+    return out;
+}
+
+static std::vector<Digest> fetch_digests(Context &c, const void *src_local, const std::vector<ShardLocation> &loc) {
+    const size_t count = loc.size();
+    std::vector<Digest> out(count);
+    if (count == 0) return out;
+    std::vector<uint64_t> idx(count);
+    std::vector<int> owners(count);
+    for (size_t q = 0; q < count; q++) { owners[q] = loc[q].owner; idx[q] = (loc[q].owner == c.rank) ? loc[q].index : 0; }
+    DevBuf d_idx(count * 8), d_out(count * 32);
+    DG_CUDA(cudaMemcpyAsync(d_idx.p, idx.data(), count * 8, cudaMemcpyHostToDevice, c.stream));
+    gather32(c, src_local, d_idx.as<unsigned long long>(), (int)count, d_out.p);
+    std::vector<uint8_t> bytes = exchange_owned(c, d_out.p, count, 32, owners);
+    memcpy(out.data(), bytes.data(), bytes.size());
+    return out;
+}
+
+std::vector<Digest> ShardedTree::fetch_nodes(Context &c, const std::vector<uint64_t> &heap_indices) const {
+    std::vector<Digest> out(heap_indices.size());
+    std::vector<uint64_t> up_idx;
+    std::vector<size_t> up_pos, lo_pos;
+    std::vector<ShardLocation> lo_loc;
+    for (size_t q = 0; q < heap_indices.size(); q++) {
+        ShardLocation l = geom.node(heap_indices[q]);
+        if (l.upper) { up_idx.push_back(l.index); up_pos.push_back(q); }
+        else { lo_loc.push_back(l); lo_pos.push_back(q); }
+    }
+    if (!up_idx.empty()) {   // replicated: purely local
+        DevBuf d_idx(up_idx.size() * 8), d_out(up_idx.size() * 32);
+        DG_CUDA(cudaMemcpyAsync(d_idx.p, up_idx.data(), up_idx.size() * 8, cudaMemcpyHostToDevice, c.stream));
+        gather32(c, upper.p, d_idx.as<unsigned long long>(), (int)up_idx.size(), d_out.p);
+        std::vector<Digest> got(up_idx.size());
+        DG_CUDA(cudaMemcpyAsync(got.data(), d_out.p, got.size() * 32, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+        for (size_t i = 0; i < got.size(); i++) out[up_pos[i]] = got[i];
+    }
+    if (!lo_loc.empty()) {
+        std::vector<Digest> got = fetch_digests(c, local_nodes.p, lo_loc);
+        for (size_t i = 0; i < got.size(); i++) out[lo_pos[i]] = got[i];
+    }
+    return out;
+}
+
+std::vector<Digest> ShardedTree::fetch_items(Context &c, const std::vector<uint64_t> &item_indices) const {
+    std::vector<ShardLocation> loc;
+    for (uint64_t i : item_indices) loc.push_back(geom.item(i));
+    return fetch_digests(c, items_local, loc);
+}
+
+}  // namespace dg

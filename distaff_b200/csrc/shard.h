@@ -1,0 +1,51 @@
+// Coset-sharded commitment trees and owner-based fetches (multi-GPU).
+//
+// A committed matrix has its level-0 items (row hashes for the trace tree, first-level nodes for the constraint tree) indexed
+// i = (k * G + g) * blk + j : rank g owns, for every k < n, the aligned block of blk = 2^log_blk consecutive items.  Each
+// rank builds the n complete subtrees over its blocks, the n subtree roots per rank are all-gathered, interleaved into the
+// level with n*G nodes, and the upper tree is finished redundantly on every rank (so all ranks hold the same root).
+// With G == 1 the same code runs without communication.
+#pragma once
+#include <array>
+#include "common.cuh"
+
+namespace dg {
+
+typedef std::array<uint8_t, 32> Digest;
+
+struct ShardLocation { int owner; bool upper; uint64_t index; };   // upper: index into the replicated upper heap, else local heap / item index
+
+struct ShardGeom {
+    uint64_t n;          // number of blocks per rank
+    int log_blk;         // items per block
+    int log_g;           // log2(world)
+    uint64_t items() const { return (n << log_blk) << log_g; }
+    // level-0 item i -> owner and index into the owner's local item array ([k][j])
+    ShardLocation item(uint64_t i) const;
+    // internal node with global heap index h (1 <= h < items())
+    ShardLocation node(uint64_t h) const;
+};
+
+struct ShardedTree {
+    ShardGeom geom;
+    const void *items_local = nullptr;   // n * blk digests, [k][j]
+    DevBuf local_nodes;                  // heap over the local items (valid for levels with >= n nodes)
+    DevBuf upper;                        // replicated heap: 2 * n * G digests, level with n*G nodes at [nG, 2nG)
+    Digest root;
+
+    void build(Context &c, const void *items_local_dev, uint64_t n, int log_blk);
+    // collective fetches (every rank passes the same lists); results in request order
+    std::vector<Digest> fetch_nodes(Context &c, const std::vector<uint64_t> &heap_indices) const;
+    std::vector<Digest> fetch_items(Context &c, const std::vector<uint64_t> &item_indices) const;
+};
+
+// owner-based exchange: every rank has filled `local` (count items of item_bytes) with the entries it owns; returns, for each
+// request q, the entry produced by owners[q]
+std::vector<uint8_t> exchange_owned(Context &c, const void *d_local, size_t count, size_t item_bytes, const std::vector<int> &owners);
+
+void merkle_build_partial(Context &c, const void *leaves, void *nodes, unsigned long long L, unsigned long long stop);
+void interleave_roots(Context &c, const void *gathered, void *upper, unsigned long long n, int log_g);
+void transpose_cosets(Context &c, const fe *in, fe *out, int log_n, int log_c, int batch);   // [batch][2^log_c][n] -> [batch][n][2^log_c]
+void constraint_items_local(Context &c, const fe *evals_local, int log_n, int log_nc, void *items);   // [k][c4_local] digests
+
+}  // namespace dg

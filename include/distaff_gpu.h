@@ -106,6 +106,17 @@ int dg_dev_hash_rows(const void *d_ext, uint32_t width, uint32_t log_n, uint32_t
 /* writes > L2-size scratch to evict the L2 between timed iterations */
 int dg_dev_flush_l2(void);
 
+/* ---- multi-GPU: one process per GPU, the proof of ONE trace is sharded by LDE coset ranges over `world` ranks ----------------
+ * Every rank calls dg_prove / dg_prove_device with the SAME trace and options; every rank returns the same proof bytes.
+ * Rank 0 obtains the 128-byte NCCL id, the host distributes it (e.g. torch.distributed broadcast), all ranks call dg_comm_init. */
+int dg_comm_unique_id(uint8_t id128[128]);
+int dg_comm_init(int rank, int world /* 1, 2, 4 or 8 */, const uint8_t id128[128]);
+int dg_comm_finalize(void);
+/* index algebra of the sharded Merkle trees, exported for CPU tests: locates level-0 item `index` (is_node = 0) or the internal
+ * node with global heap index `index` (is_node = 1) of a tree with n blocks of 2^log_blk items per rank over 2^log_g ranks;
+ * out = {owner rank or -1 if replicated, 1 if in the replicated upper heap else 0, local index} */
+int dg_host_shard_locate(uint64_t n, int log_blk, int log_g, int is_node, uint64_t index, int64_t out[3]);
+
 /* ---- host-side Fiat-Shamir glue, exported so that it can be unit-tested without a GPU (none of these touch the device) ---- */
 /* field::prng_vector (field.rs:271-275): count draws of StdRng::from_seed(seed) through Uniform(0..M) */
 int dg_host_prng_vector(const uint8_t seed[32], uint64_t count, uint8_t *out16);

@@ -124,3 +124,46 @@ def test_periodic_tables_interpolate_the_round_constants(L):
                     den = den * (xs[i] - xs[j]) % M
             acc = (acc + ys[i] * num * pow(den, M - 2, M)) % M
         assert acc == int(t[s, col])
+
+
+def test_sharded_tree_index_algebra(L):
+    """ShardGeom (distaff_b200/csrc/shard.cu) against a brute-force model: build the global heap of item ids and the per-rank local
+    heaps, then check that every global node / item is found at the location the product code computes."""
+    import ctypes
+    out = (ctypes.c_int64 * 3)()
+    for n, log_blk, log_g in ((4, 2, 1), (8, 3, 2), (4, 2, 3), (16, 0, 3), (8, 5, 0), (2, 1, 2)):
+        blk, G = 1 << log_blk, 1 << log_g
+        total = n * blk * G
+        # global tree: node = frozenset of the level-0 items below it
+        level = [frozenset([i]) for i in range(total)]
+        glob = {}
+        size = total
+        items_level = level
+        while size > 1:
+            level = [level[2 * i] | level[2 * i + 1] for i in range(size // 2)]
+            size //= 2
+            for o, s_ in enumerate(level):
+                glob[size + o] = s_
+        # local trees: rank g holds items i = (k*G + g)*blk + j at local index k*blk + j
+        local = []
+        for g in range(G):
+            its = [frozenset([(k * G + g) * blk + j]) for k in range(n) for j in range(blk)]
+            heap = {}
+            lv, sz = its, n * blk
+            while sz > n:
+                lv = [lv[2 * i] | lv[2 * i + 1] for i in range(sz // 2)]
+                sz //= 2
+                for o, s_ in enumerate(lv):
+                    heap[sz + o] = s_
+            local.append((its, heap))
+        for i in range(total):
+            assert L.dg_host_shard_locate(n, log_blk, log_g, 0, i, out) == 0
+            owner, upper, idx = out[0], out[1], out[2]
+            assert upper == 0 and local[owner][0][idx] == frozenset([i])
+        for h in range(1, total):
+            assert L.dg_host_shard_locate(n, log_blk, log_g, 1, h, out) == 0
+            owner, upper, idx = out[0], out[1], out[2]
+            if upper:
+                assert h < 2 * n * G and idx == h
+            else:
+                assert local[owner][1][idx] == glob[h], (n, log_blk, log_g, h)
