@@ -40,4 +40,11 @@ def small_programs():
     P["if_else0"] = hostvm.execute("begin push.3 push.5 read if.true add else mul end end", secret_a=[0], num_outputs=1)
     P["nested"] = hostvm.execute("begin push.2 block push.3 block push.4 add end mul end add end", public_inputs=[1], num_outputs=1)
     P["collatz3"] = hostvm.collatz(3)                                                                  # loop + switch + isodd
+    # wider register files: user stack deeper than 16, context depth 3, nested loops (loop depth 2)
+    P["deep_stack"] = hostvm.execute("begin " + " ".join(f"push.{i + 1}" for i in range(22)) + " add mul swap.4 roll.8 dup.4 drop.8 end",
+                                     public_inputs=[9, 8, 7], num_outputs=4)
+    P["deep_ctx"] = hostvm.execute("begin push.1 block push.2 block push.3 block push.4 add end add end add end end", num_outputs=1)
+    P["nested_loops"] = hostvm.execute(
+        "begin push.2 push.1 while.true push.3 push.1 while.true push.1 neg add dup push.0 ne end drop push.1 neg add dup push.0 ne end end",
+        num_outputs=1)
     return P
