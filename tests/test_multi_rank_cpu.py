@@ -67,7 +67,8 @@ for i in range(total):
         assert mine[out[2]] == items[i]
 dist.barrier()
 dist.destroy_process_group()
-print("RANK_OK", rank)
+sys.stdout.write("RANK_OK_%d\n" % rank)
+sys.stdout.flush()
 '''
 
 
@@ -86,7 +87,7 @@ def test_sharded_commitment_world_size_2(tmp_path):
     script.write_text(WORKER % {"root": ROOT})
     r = _torchrun([str(script)])
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "RANK_OK 0" in r.stdout and "RANK_OK 1" in r.stdout
+    assert "RANK_OK_0" in r.stdout and "RANK_OK_1" in r.stdout
 
 
 def test_reference_arm_under_torchrun_prints_one_line():
