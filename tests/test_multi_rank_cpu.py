@@ -67,7 +67,7 @@ for i in range(total):
         assert mine[out[2]] == items[i]
 dist.barrier()
 dist.destroy_process_group()
-sys.stdout.write("RANK_OK_%d\n" % rank)
+sys.stdout.write("RANK_OK_" + str(rank) + "\n")
 sys.stdout.flush()
 '''
 
