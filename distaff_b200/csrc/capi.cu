@@ -123,7 +123,7 @@ int dg_dev_flush_l2(void) {
         Context &c = ctx();
         static DevBuf scratch;
         const size_t bytes = (size_t)256 << 20;
-        scratch.ensure(bytes);
+        scratch.ensure(bytes, true);
         fill_kernel<<<(unsigned)(bytes / 16 / 256), 256, 0, c.stream>>>(scratch.as<uint4>(), bytes / 16, 7u); c.launches++;
         DG_CUDA(cudaGetLastError());
         DG_CUDA(cudaStreamSynchronize(c.stream));
@@ -137,7 +137,7 @@ int dg_dev_ntt(void *d_values, uint32_t log_n, uint32_t batch, int inverse, floa
         std::lock_guard<std::mutex> lk(c.mu);
         c.twiddle(log_n, inverse != 0);       // table setup outside the timed region
         if (log_n > 20) c.twiddle(log_n - (log_n + 2) / 3, inverse != 0);
-        c.ntt_tmp.ensure(((size_t)16 << log_n) * std::min<size_t>(batch, std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)16 << log_n))));
+        c.ntt_tmp.ensure(((size_t)16 << log_n) * std::min<size_t>(batch, std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)16 << log_n))), true);
         EventTimer t(c.stream, ms);
         ntt_batch(c, (const fe *)d_values, (fe *)d_values, log_n, batch, (size_t)1 << log_n, (size_t)1 << log_n, inverse != 0);
         t.stop();

@@ -33,27 +33,66 @@ struct Error : public std::runtime_error {
 // stream on which DevBuf allocations are ordered (the context's stream once it exists)
 cudaStream_t &alloc_stream();
 
-// RAII device buffer backed by the stream-ordered allocator (cudaMallocAsync): after the first proof the pool serves every
-// request without touching the driver, so per-proof buffers (tens of GB at 2^20 steps) cost microseconds to obtain
+// Per-proof arena: a proof's buffers (tens of GB at 2^20 steps) are carved out of one device allocation with a bump pointer, so a
+// proof performs no driver allocation at all.  The first proof of a given size runs on the stream-ordered pool and records how
+// much it needed; the arena is then (re)sized for the following proofs.  Persistent objects (twiddle tables, NTT scratch) never
+// come from the arena.
+struct Arena {
+    void *base = nullptr;
+    size_t cap = 0, off = 0, counted = 0;
+    bool active = false, counting = false;
+    void *take(size_t n) {
+        const size_t a = (n + 255) & ~(size_t)255;
+        if (off + a > cap) return nullptr;
+        void *p = (uint8_t *)base + off;
+        off += a;
+        return p;
+    }
+};
+Arena &arena();
+
+// RAII device buffer: arena (inside a proof), else stream-ordered allocator (cudaMallocAsync with a retained pool)
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
+    bool from_arena = false;
     DevBuf() {}
     explicit DevBuf(size_t n) { alloc(n); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
-    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; } return *this; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), from_arena(o.from_arena) { o.p = nullptr; o.bytes = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; from_arena = o.from_arena; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
     ~DevBuf() { release(); }
-    void alloc(size_t n) {
+    void alloc(size_t n, bool persistent = false) {
         release();
         if (n == 0) return;
+        Arena &a = arena();
+        if (!persistent) {
+            if (a.counting) a.counted += (n + 255) & ~(size_t)255;
+            if (a.active) {
+                p = a.take(n);
+                if (p) { bytes = n; from_arena = true; return; }
+            }
+        }
         DG_CUDA(cudaMallocAsync(&p, n, alloc_stream()));
         bytes = n;
+        from_arena = false;
     }
-    void ensure(size_t n) { if (bytes < n) alloc(n); }
-    void release() { if (p) cudaFreeAsync(p, alloc_stream()); p = nullptr; bytes = 0; }
+    void ensure(size_t n, bool persistent = false) { if (bytes < n) alloc(n, persistent); }
+    void release() {
+        if (p && !from_arena) cudaFreeAsync(p, alloc_stream());
+        p = nullptr; bytes = 0; from_arena = false;
+    }
     template <typename T> T *as() const { return (T *)p; }
+};
+
+// brackets one proof: activates the arena when it is large enough, otherwise measures the proof so that the next one fits
+struct ArenaScope {
+    ArenaScope();
+    ~ArenaScope();
 };
 
 // two-level table of powers of a root of unity of order 2^log_order:
@@ -72,12 +111,14 @@ struct Context {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // host->device uploads that overlap compute (prover.cu stage 1)
     std::mutex mu;
     // small root tables for the in-shared-memory transforms: roots[inv][l] = w_{2^l}^m, m < 2^(l-1), l = 1..MAX_LOG_L
     DevBuf small_roots[2];
     size_t small_root_offset[16];
     std::map<int, TwiddleTable> twiddles;   // key = log_order * 2 + inverse
-    DevBuf ntt_tmp;                         // scratch of the multi-pass transforms
+    DevBuf ntt_tmp;
+    DevBuf upload_buf;                       // device copy of a host trace (dg_prove), kept between proofs                         // scratch of the multi-pass transforms
     std::string last_error;
     unsigned long long launches = 0;        // kernels launched by this library (bench.py's gpu_launches)
     int rank = 0, world = 1;                // multi-GPU sharding (comm.cu); world == 1: no communication

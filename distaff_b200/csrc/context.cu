@@ -25,6 +25,36 @@ __global__ void power_table_kernel(fe *out, fe step, unsigned count) {
 static cudaStream_t g_alloc_stream = nullptr;
 cudaStream_t &alloc_stream() { return g_alloc_stream; }
 
+static Arena g_arena;
+Arena &arena() { return g_arena; }
+
+ArenaScope::ArenaScope() {
+    Arena &a = g_arena;
+    a.off = 0;
+    a.counted = 0;
+    a.counting = true;
+    a.active = a.base != nullptr && !getenv("DG_NO_ARENA");
+}
+ArenaScope::~ArenaScope() {
+    Arena &a = g_arena;
+    a.counting = false;
+    const bool overflowed = a.counted > a.cap;
+    a.active = false;
+    if (overflowed && !getenv("DG_NO_ARENA")) {          // grow for the next proof of this size (driver call, outside the timed path)
+        cudaStreamSynchronize(alloc_stream());
+        if (a.base) cudaFree(a.base);
+        a.base = nullptr;
+        a.cap = 0;
+        const size_t want = a.counted + (a.counted >> 4) + (64 << 20);
+        cudaMemPool_t pool;                               // hand the measuring proof's pool memory back before taking the arena
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        if (cudaMalloc(&a.base, want) == cudaSuccess) a.cap = want;
+        else { a.base = nullptr; cudaGetLastError(); }
+    }
+}
+
 static std::once_flag g_once;
 static Context *g_ctx = nullptr;
 static int g_device = -1;
@@ -42,6 +72,7 @@ static void build_context(int device) {
     DG_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     DG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    DG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     g_alloc_stream = c->stream;
     {   // keep freed blocks in the pool instead of returning them to the driver between proofs
         cudaMemPool_t pool;
@@ -56,7 +87,7 @@ static void build_context(int device) {
     for (int l = 1; l <= MAX_LOG_L; l++) { c->small_root_offset[l] = total; total += (size_t)1 << l; }
     c->small_root_offset[0] = 0;
     for (int inv = 0; inv < 2; inv++) {
-        c->small_roots[inv].alloc(total * sizeof(fe));
+        c->small_roots[inv].alloc(total * sizeof(fe), true);
         DG_CUDA(cudaMemsetAsync(c->small_roots[inv].p, 0, total * sizeof(fe), c->stream));
         for (int l = 1; l <= MAX_LOG_L; l++) {
             fe w = host_root_of_unity(l);
@@ -97,7 +128,8 @@ const fe *Context::single_table(int log_order) {
     DG_REQUIRE(log_order <= 20, "single-level table too large");
     auto it = single_tables.find(log_order);
     if (it == single_tables.end()) {
-        DevBuf t(((size_t)1 << log_order) * sizeof(fe));
+        DevBuf t;
+        t.alloc(((size_t)1 << log_order) * sizeof(fe), true);
         const unsigned cnt = 1u << log_order;
         power_table_kernel<<<(cnt + 127) / 128, 128, 0, stream>>>(t.as<fe>(), host_root_of_unity(log_order), cnt); launches++;
         DG_CUDA(cudaGetLastError());
@@ -117,8 +149,8 @@ TwiddleRef Context::twiddle(int log_order, bool inverse) {
         fe w = host_root_of_unity(log_order);
         if (inverse) w = host_inv(w);
         fe whi = host_pow(w, lo_n);
-        t.lo.alloc(lo_n * sizeof(fe));
-        t.hi.alloc(hi_n * sizeof(fe));
+        t.lo.alloc(lo_n * sizeof(fe), true);
+        t.hi.alloc(hi_n * sizeof(fe), true);
         power_table_kernel<<<(lo_n + 127) / 128, 128, 0, stream>>>(t.lo.as<fe>(), w, lo_n); launches++;
         power_table_kernel<<<(hi_n + 127) / 128, 128, 0, stream>>>(t.hi.as<fe>(), whi, hi_n); launches++;
         DG_CUDA(cudaGetLastError());

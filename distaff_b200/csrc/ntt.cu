@@ -260,7 +260,7 @@ static void run_transform(Context &c, const fe *src, fe *dst, int log_n, bool in
     fe *tmp = nullptr;
     long long tmp_stride_y = n, tmp_stride_z = n * by;
     if (np > 1) {
-        c.ntt_tmp.ensure((size_t)n * by * bz * sizeof(fe));
+        c.ntt_tmp.ensure((size_t)n * by * bz * sizeof(fe), true);
         tmp = c.ntt_tmp.as<fe>();
     }
 

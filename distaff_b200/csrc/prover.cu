@@ -113,9 +113,11 @@ struct FriLayerDev {
 
 }  // namespace
 
-Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t length, uint32_t ctx_depth, uint32_t loop_depth,
-                    const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs, const dg_options_t &opt,
-                    dg_prove_stats_t *stats, float h2d_ms) {
+// d_regs: register traces in device memory; when `host_cols` is given they are not there yet: column chunks are uploaded on the
+// copy stream while the previous chunk is being interpolated and extended (the upload hides behind the LDE)
+static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols, uint32_t width, uint64_t length, uint32_t ctx_depth,
+                         uint32_t loop_depth, const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs,
+                         const dg_options_t &opt, dg_prove_stats_t *stats) {
     // ---- argument checks (trace_table.rs:23-58, options.rs:29-50, lib.rs:33-34) -----------------------------------------------
     const uint64_t n = length, b = opt.extension_factor;
     DG_REQUIRE(opt.hash_id == 0, "unsupported hash function (only blake3 is serialisable, options.rs:107)");
@@ -137,6 +139,7 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
     if (n_inputs) memcpy(inputs.data(), inputs16, n_inputs * 16);
     if (n_outputs) memcpy(outputs.data(), outputs16, n_outputs * 16);
 
+    ArenaScope arena_scope;                   // all DevBufs below come from the per-proof arena (no driver allocation inside a proof)
     StageClock clk(c.stream);
     const unsigned long long launches0 = c.launches;
     Proof *proof = new Proof();
@@ -154,8 +157,33 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
     // ---- 1: extend execution trace ---------------------------------------------------------------------------------------------------
     clk.mark(0);
     DevBuf polys((size_t)w * n * 16), ext((size_t)w * N_loc * 16);
-    ntt_batch(c, d_regs, polys.as<fe>(), log_n, w, n, n, true);
-    lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
+    if (!host_cols) {
+        ntt_batch(c, d_regs, polys.as<fe>(), log_n, w, n, n, true);
+        lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
+    } else {
+        const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>(w, ((uint64_t)1 << 25) / (n * 16)));   // ~32 MB per upload
+        std::vector<cudaEvent_t> done((w + chunk - 1) / chunk);
+        {   // the destination comes from the stream-ordered pool of the compute stream: order the copy stream after it
+            cudaEvent_t ready;
+            DG_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+            DG_CUDA(cudaEventRecord(ready, c.stream));
+            DG_CUDA(cudaStreamWaitEvent(c.copy_stream, ready, 0));
+            cudaEventDestroy(ready);
+        }
+        for (size_t i = 0; i < done.size(); i++) {           // enqueue every upload first: the copy engine runs ahead of the compute stream
+            DG_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+            for (int j = (int)i * chunk; j < std::min(w, (int)(i + 1) * chunk); j++)
+                DG_CUDA(cudaMemcpyAsync(d_regs + (size_t)j * n, host_cols[j], n * 16, cudaMemcpyHostToDevice, c.copy_stream));
+            DG_CUDA(cudaEventRecord(done[i], c.copy_stream));
+        }
+        for (size_t i = 0; i < done.size(); i++) {
+            const int j0 = (int)i * chunk, cols = std::min(w, j0 + chunk) - j0;
+            DG_CUDA(cudaStreamWaitEvent(c.stream, done[i], 0));
+            ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, cols, n, n, true);
+            lde_batch(c, polys.as<fe>() + (size_t)j0 * n, ext.as<fe>() + (size_t)j0 * N_loc, log_n, log_b, 1, cols, n, N_loc, c0, (unsigned)nc);
+        }
+        for (auto &e : done) cudaEventDestroy(e);
+    }
 
     // ---- 2: trace Merkle tree ----------------------------------------------------------------------------------------------------------
     clk.mark(1);
@@ -176,7 +204,7 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
     static DevBuf d_periodic;
     if (!d_periodic.p) {
         std::vector<fe> per = fs::periodic_tables();
-        d_periodic.alloc(per.size() * 16);
+        d_periodic.alloc(per.size() * 16, true);
         h2d(c, d_periodic.p, per.data(), per.size() * 16);
     }
     const size_t T = cc.coefA.size(), nb = cc.bAi.size();
@@ -462,33 +490,27 @@ Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t lengt
     proof->bytes = std::move(out.b);
     if (stats) {
         for (int i = 0; i < 9; i++) stats->stage_ms[i] = clk.between(i, i + 1);
-        stats->h2d_ms = h2d_ms;
-        stats->total_ms = clk.between(0, 9) + h2d_ms;
+        stats->h2d_ms = 0.0f;                        // host variant: uploads overlap stage 1 and are part of stage_ms[0]
+        stats->total_ms = clk.between(0, 9);
         stats->kernel_launches = c.launches - launches0;
     }
     return guard.release();
+}
+
+Proof *prove_device(Context &c, const fe *d_regs, uint32_t width, uint64_t length, uint32_t ctx_depth, uint32_t loop_depth,
+                    const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs, const dg_options_t &opt,
+                    dg_prove_stats_t *stats, float) {
+    return prove_core(c, const_cast<fe *>(d_regs), nullptr, width, length, ctx_depth, loop_depth, inputs16, n_inputs, outputs16, n_outputs, opt, stats);
 }
 
 Proof *prove_host(Context &c, const dg_trace_t &trace, const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16,
                   uint32_t n_outputs, const dg_options_t &opt, dg_prove_stats_t *stats) {
     DG_REQUIRE(trace.columns && trace.width >= 16 && trace.width < 128, "invalid trace");
     DG_REQUIRE(trace.length >= 16 && (trace.length & (trace.length - 1)) == 0, "execution trace length must be a power of 2 and at least 16");
-    const size_t col_bytes = (size_t)trace.length * 16;
-    DevBuf d_regs(col_bytes * trace.width);
-    cudaEvent_t e0, e1;
-    DG_CUDA(cudaEventCreate(&e0)); DG_CUDA(cudaEventCreate(&e1));
-    DG_CUDA(cudaEventRecord(e0, c.stream));
-    for (uint32_t j = 0; j < trace.width; j++) {
-        DG_REQUIRE(trace.columns[j] != nullptr, "null register column");
-        DG_CUDA(cudaMemcpyAsync((uint8_t *)d_regs.p + j * col_bytes, trace.columns[j], col_bytes, cudaMemcpyHostToDevice, c.stream));
-    }
-    DG_CUDA(cudaEventRecord(e1, c.stream));
-    DG_CUDA(cudaEventSynchronize(e1));
-    float h2d_ms = 0;
-    cudaEventElapsedTime(&h2d_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    return prove_device(c, d_regs.as<fe>(), trace.width, trace.length, trace.ctx_depth, trace.loop_depth, inputs16, n_inputs, outputs16,
-                        n_outputs, opt, stats, h2d_ms);
+    for (uint32_t j = 0; j < trace.width; j++) DG_REQUIRE(trace.columns[j] != nullptr, "null register column");
+    c.upload_buf.ensure((size_t)trace.length * 16 * trace.width, true);
+    return prove_core(c, c.upload_buf.as<fe>(), trace.columns, trace.width, trace.length, trace.ctx_depth, trace.loop_depth, inputs16, n_inputs,
+                      outputs16, n_outputs, opt, stats);
 }
 
 }  // namespace dg
