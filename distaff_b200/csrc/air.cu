@@ -94,22 +94,15 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
     const int cl = P.cl, ll = P.ll, sl = P.sl;
     const int ctx_off = 15, loop_off = 15 + P.ctx_depth, stk_off = 15 + P.ctx_depth + P.loop_depth;
 
-    // ---- boundary constraints: dot products of the current row with per-register coefficients ----------------------------
-    fe biA = ZERO, biB = ZERO, bfA = ZERO, bfB = ZERO;
+    // ---- the two rows.  Boundary constraints are not evaluated here: their numerators are assembled in coefficient form from the
+    //      trace polynomials (poly.cu: boundary_coeffs), which is 8x less work than evaluating them on this domain.
     fe cur_dec[15], nxt_dec[15];
     fe c_ctx[16], n_ctx[16], c_loop[8], n_loop[8], o[32], nw[32];
     {
-        const int nb = P.n_boundary_regs;
-        for (int j = 0; j < nb; j++) {
-            fe v = cur_p[(unsigned long long)j * N];
-            biA = fe_add(biA, fe_mul(v, P.bAi[j])); biB = fe_add(biB, fe_mul(v, P.bBi[j]));
-            bfA = fe_add(bfA, fe_mul(v, P.bAf[j])); bfB = fe_add(bfB, fe_mul(v, P.bBf[j]));
-            if (j < 15) cur_dec[j] = v;
-            else if (j < loop_off) c_ctx[j - ctx_off] = v;
-            else if (j < stk_off) c_loop[j - loop_off] = v;
-            else o[j - stk_off] = v;
-        }
-        for (int j = nb; j < P.w; j++) o[j - stk_off] = cur_p[(unsigned long long)j * N];   // stack registers without boundary constraints
+        for (int j = 0; j < 15; j++) cur_dec[j] = cur_p[(unsigned long long)j * N];
+        for (int j = 0; j < P.ctx_depth; j++) c_ctx[j] = cur_p[(unsigned long long)(ctx_off + j) * N];
+        for (int j = 0; j < P.loop_depth; j++) c_loop[j] = cur_p[(unsigned long long)(loop_off + j) * N];
+        for (int j = 0; j < P.stack_depth; j++) o[j] = cur_p[(unsigned long long)(stk_off + j) * N];
         for (int j = P.ctx_depth; j < cl; j++) c_ctx[j] = ZERO;
         for (int j = P.loop_depth; j < ll; j++) c_loop[j] = ZERO;
         for (int j = P.stack_depth; j < sl; j++) o[j] = ZERO;
@@ -121,13 +114,6 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         for (int j = 0; j < P.stack_depth; j++) nw[j] = nxt_p[(unsigned long long)(stk_off + j) * N];
         for (int j = P.stack_depth; j < sl; j++) nw[j] = ZERO;
     }
-    {
-        fe xp = tw_pow(P.twN, lde_index * P.b_adj);                  // x^(6n+2), x = w_N^lde_index
-        fe i_res = fe_add(fe_sub(biA, P.KiA), fe_mul(fe_sub(biB, P.KiB), xp));
-        fe f_res = fe_add(fe_sub(bfA, P.KfA), fe_mul(fe_sub(bfB, P.KfB), xp));
-        P.i_ev[out_idx] = i_res;
-        P.f_ev[out_idx] = f_res;
-    }
 
     // ---- op flags (trace_state.rs:281-350) ----------------------------------------------------------------------------------
     const fe op_counter = cur_dec[0];
@@ -135,15 +121,16 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
     const fe *nsp = nxt_dec + 1, *ncf = nxt_dec + 5;
     fe cff[8], ldf[32], hdf[4];
     {
-        fe n0 = bnot(cf[0]), n1 = bnot(cf[1]), n2 = bnot(cf[2]);
-        fe a0 = fe_mul(n0, n1), a1 = fe_mul(cf[0], n1), a2 = fe_mul(n0, cf[1]), a3 = fe_mul(cf[0], cf[1]);
-        cff[0] = fe_mul(a0, n2); cff[1] = fe_mul(a1, n2); cff[2] = fe_mul(a2, n2); cff[3] = fe_mul(a3, n2);
+        // products of bits and negated bits; f*(1 - x) is computed as f - f*x (one multiplication per pair of flags)
+        fe a3 = fe_mul(cf[0], cf[1]);
+        fe a1 = fe_sub(cf[0], a3), a2 = fe_sub(cf[1], a3), a0 = fe_sub(bnot(cf[0]), a2);
         cff[4] = fe_mul(a0, cf[2]); cff[5] = fe_mul(a1, cf[2]); cff[6] = fe_mul(a2, cf[2]); cff[7] = fe_mul(a3, cf[2]);
+        cff[0] = fe_sub(a0, cff[4]); cff[1] = fe_sub(a1, cff[5]); cff[2] = fe_sub(a2, cff[6]); cff[3] = fe_sub(a3, cff[7]);
     }
     fe hdf_raw0;
     {
-        fe n0 = bnot(hd[0]), n1 = bnot(hd[1]);
-        hdf[0] = fe_mul(n0, n1); hdf[1] = fe_mul(hd[0], n1); hdf[2] = fe_mul(n0, hd[1]); hdf[3] = fe_mul(hd[0], hd[1]);
+        hdf[3] = fe_mul(hd[0], hd[1]);
+        hdf[1] = fe_sub(hd[0], hdf[3]); hdf[2] = fe_sub(hd[1], hdf[3]); hdf[0] = fe_sub(bnot(hd[0]), hdf[2]);
         hdf_raw0 = hdf[0];
         hdf[0] = fe_mul(hdf[0], ld[0]);      // PUSH flag adjustment
     }
@@ -262,19 +249,17 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
     }
 
     {
-        fe n0 = bnot(ld[0]), n1 = bnot(ld[1]);
-        ldf[0] = fe_mul(n0, n1); ldf[1] = fe_mul(ld[0], n1);
-        ldf[2] = fe_mul(n0, cf[1]);                                   // sic (trace_state.rs:301)
+        fe n0 = bnot(ld[0]);
         ldf[3] = fe_mul(ld[0], ld[1]);
-        fe n2 = bnot(ld[2]);
+        ldf[1] = fe_sub(ld[0], ldf[3]);                               // ld0 (1 - ld1)
+        ldf[0] = fe_sub(n0, fe_sub(ld[1], ldf[3]));                   // (1 - ld0)(1 - ld1)
+        ldf[2] = fe_mul(n0, cf[1]);                                   // sic (trace_state.rs:301)
 #pragma unroll
-        for (int i = 0; i < 4; i++) { ldf[4 + i] = fe_mul(ldf[i], ld[2]); ldf[i] = fe_mul(ldf[i], n2); }
-        fe n3 = bnot(ld[3]);
+        for (int i = 0; i < 4; i++) { ldf[4 + i] = fe_mul(ldf[i], ld[2]); ldf[i] = fe_sub(ldf[i], ldf[4 + i]); }
 #pragma unroll
-        for (int i = 0; i < 8; i++) { ldf[8 + i] = fe_mul(ldf[i], ld[3]); ldf[i] = fe_mul(ldf[i], n3); }
-        fe n4 = bnot(ld[4]);
+        for (int i = 0; i < 8; i++) { ldf[8 + i] = fe_mul(ldf[i], ld[3]); ldf[i] = fe_sub(ldf[i], ldf[8 + i]); }
 #pragma unroll
-        for (int i = 0; i < 16; i++) { ldf[16 + i] = fe_mul(ldf[i], ld[4]); ldf[i] = fe_mul(ldf[i], n4); }
+        for (int i = 0; i < 16; i++) { ldf[16 + i] = fe_mul(ldf[i], ld[4]); ldf[i] = fe_sub(ldf[i], ldf[16 + i]); }
     }
     fe begin_flag, noop_flag;
     {

@@ -237,6 +237,37 @@ void lincomb2(Context &c, const fe *polys, unsigned long long n, int w, const fe
     DG_CUDA(cudaGetLastError());
 }
 
+// Boundary-constraint numerators in coefficient form.  The reference evaluates, at every point x of the 8n-point constraint domain,
+//   I(x) = sum_j (T_j(x) - in_j) (a_j + b_j x^adj)            (evaluator.rs:181-326, adj = 6n + 2)
+// and interpolates the evaluations afterwards (constraint_poly.rs).  I has degree n - 1 + adj < 8n, so the interpolant IS the polynomial
+//   I = (sum_j a_j T_j - Ka) + x^adj (sum_j b_j T_j - Kb),     Ka = sum_j a_j in_j,  Kb = sum_j b_j in_j
+// whose coefficients are two linear combinations of the trace polynomials' coefficients: n*nb multiplications instead of 8n*nb.
+// coef = [a_init | b_init | a_final | b_final], nb entries each; ic / fc receive the 8n coefficients of the first / last step numerators.
+__global__ void boundary_coeffs_kernel(const fe *__restrict__ polys, unsigned long long n, int nb, const fe *__restrict__ coef, fe KiA, fe KiB,
+                                       fe KfA, fe KfB, unsigned long long adj, fe *__restrict__ ic, fe *__restrict__ fc) {
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    fe ia = fe_make(0, 0), ib = ia, fa = ia, fb = ia;
+    for (int j = 0; j < nb; j++) {
+        const fe v = polys[(unsigned long long)j * n + k];
+        ia = fe_add(ia, fe_mul(v, coef[j]));
+        ib = fe_add(ib, fe_mul(v, coef[nb + j]));
+        fa = fe_add(fa, fe_mul(v, coef[2 * nb + j]));
+        fb = fe_add(fb, fe_mul(v, coef[3 * nb + j]));
+    }
+    if (k == 0) { ia = fe_sub(ia, KiA); ib = fe_sub(ib, KiB); fa = fe_sub(fa, KfA); fb = fe_sub(fb, KfB); }
+    const fe zero = fe_make(0, 0);
+    ic[k] = ia; fc[k] = fa;
+    ic[adj + k] = ib; fc[adj + k] = fb;
+    // the gaps [n, adj) and [adj + n, 8n): 5n + 2 + (n - 2) = 6n entries, six per thread
+    for (unsigned long long q = n + k; q < 8 * n; q += n)
+        if (q < adj || q >= adj + n) { ic[q] = zero; fc[q] = zero; }
+}
+void boundary_coeffs(Context &c, const fe *polys, unsigned long long n, int nb, const fe *coef, fe KiA, fe KiB, fe KfA, fe KfB, fe *ic, fe *fc) {
+    boundary_coeffs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(polys, n, nb, coef, KiA, KiB, KfA, KfB, 6 * n + 2, ic, fc); c.launches++;
+    DG_CUDA(cudaGetLastError());
+}
+
 // composition polynomial (trace_table.rs:241-258, constraint_poly.rs:49):
 //   comp[k] = cq[k]*kc + [k < n] (t1q[k]+t2q[k])*k1 + [inc <= k < inc+n] (t1q[k-inc]+t2q[k-inc])*k2
 __global__ void compose_kernel(const fe *__restrict__ t1q, const fe *__restrict__ t2q, const fe *__restrict__ cq, fe *__restrict__ comp,

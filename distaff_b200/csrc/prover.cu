@@ -221,26 +221,23 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         DG_CUDA(cudaStreamSynchronize(c.stream));
     }
     DG_CUDA(cudaMemsetAsync(d_violation.p, 0, 4, c.stream));
-    DevBuf evals(3 * E * 16);
+    DevBuf evals(3 * E * 16);                 // [boundary numerator, first step | boundary numerator, last step | transition combination]
     {
         const int num_c8 = 8 >> log_g;
         const uint64_t E_loc = n * num_c8;
-        DevBuf evals_loc(3 * E_loc * 16), gathered(3 * E * 16);
+        DevBuf evals_loc(E_loc * 16), gathered(E * 16);
         AirParams P;
         memset(&P, 0, sizeof P);
         P.w = w; P.ctx_depth = ctx_depth; P.loop_depth = loop_depth; P.stack_depth = stack_depth;
         P.cl = std::max<int>(ctx_depth, 1); P.ll = std::max<int>(loop_depth, 1); P.sl = std::max(stack_depth, 8);
-        P.log_n = log_n; P.log_blowup = log_b; P.n_boundary_regs = cc.n_boundary_regs;
+        P.log_n = log_n; P.log_blowup = log_b;
         P.ext = ext.as<fe>(); P.col_stride = N_loc;
         P.c8_base = g * num_c8; P.num_c8 = num_c8;
-        P.i_ev = evals_loc.as<fe>(); P.f_ev = evals_loc.as<fe>() + E_loc; P.t_ev = evals_loc.as<fe>() + 2 * E_loc;
+        P.t_ev = evals_loc.as<fe>();
         P.periodic = d_periodic.as<fe>();
         const fe *base = d_coef.as<fe>();
         P.coefA = base; P.coefB = base + T;
-        P.bAi = base + 2 * T; P.bBi = P.bAi + nb; P.bAf = P.bBi + nb; P.bBf = P.bAf + nb;
-        P.KiA = cc.KiA; P.KiB = cc.KiB; P.KfA = cc.KfA; P.KfB = cc.KfB;
         P.twN = c.twiddle(log_N, false);
-        P.b_adj = 6 * n + 2;
         static const int GROUP_DEG[6] = {2, 3, 4, 6, 7, 8};
         for (int gi = 0; gi < 6; gi++) P.inc[gi] = (8 * n - 1) - (n - 1) * GROUP_DEG[gi];
         P.violation = d_violation.as<unsigned>();
@@ -249,13 +246,12 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         unsigned violation = 0;
         d2h(c, &violation, d_violation.p, 4);
         if (violation) throw Error(DG_ERR_UNSATISFIED, "transition constraints at step " + std::to_string(violation - 1) + " were not satisfied");
-        // every rank needs all three accumulators to interpolate them: gather the coset slabs, then go to natural step order
-        for (int v = 0; v < 3; v++)
-            comm_all_gather(c, evals_loc.as<fe>() + v * E_loc, gathered.as<fe>() + v * E, E_loc * 16);
-        transpose_cosets(c, gathered.as<fe>(), evals.as<fe>(), log_n, 3, 3);
+        // every rank interpolates the transition combination: gather the coset slabs, then go to natural step order
+        comm_all_gather(c, evals_loc.as<fe>(), gathered.as<fe>(), E_loc * 16);
+        transpose_cosets(c, gathered.as<fe>(), evals.as<fe>() + 2 * E, log_n, 3, 1);
+        // boundary constraints (evaluator.rs:181-326), directly as the 8n coefficients the reference obtains by interpolation
+        boundary_coeffs(c, polys.as<fe>(), n, (int)nb, base + 2 * T, cc.KiA, cc.KiB, cc.KfA, cc.KfB, evals.as<fe>(), evals.as<fe>() + E);
     }
-    debug_dump(c, "i_evals", evals.as<fe>(), E * 16);
-    debug_dump(c, "f_evals", evals.as<fe>() + E, E * 16);
     debug_dump(c, "t_evals", evals.as<fe>() + 2 * E, E * 16);
 
     // ---- 4: convert constraint evaluations into a polynomial -----------------------------------------------------------------------------
@@ -265,7 +261,9 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
     const fe root_n = host_root_of_unity(log_n);
     const fe x_last = host_inv(root_n);                        // w_n^(n-1)   (evaluator.rs:128-131)
     {
-        ntt_batch(c, evals.as<fe>(), evals.as<fe>(), log_E, 3, E, E, true);
+        ntt_batch(c, evals.as<fe>() + 2 * E, evals.as<fe>() + 2 * E, log_E, 1, E, E, true);
+        debug_dump(c, "i_coeffs", evals.as<fe>(), E * 16);
+        debug_dump(c, "f_coeffs", evals.as<fe>() + E, E * 16);
         fe *ic = evals.as<fe>(), *fc = evals.as<fe>() + E, *tc = evals.as<fe>() + 2 * E;
         PowTable one_t(c, fe_make(1, 0), E + 1), xl_t(c, x_last, E + 1), xli_t(c, root_n, E + 1);
         syn_div(c, ic, ic, scratch.as<fe>(), E, one_t.ref(), one_t.ref(), fe_make(0, 0));            // / (x - 1)

@@ -27,13 +27,17 @@ for name in names:
     except Exception as e:
         print("  GPU prove failed:", e)
         proof = None
-    for vec in ("i_evals", "f_evals", "t_evals", "constraint_poly", "composition_poly"):
-        path = os.path.join(d, vec + ".bin")
+    # the GPU path builds the boundary numerators directly in coefficient form: compare them with the interpolated oracle evaluations
+    for vec, src in (("i_evals", "i_coeffs"), ("f_evals", "f_coeffs"), ("t_evals", "t_evals"), ("constraint_poly", "constraint_poly"),
+                     ("composition_poly", "composition_poly")):
+        path = os.path.join(d, src + ".bin")
         if not os.path.exists(path):
             print("  ", vec, "not dumped")
             continue
         got = np.fromfile(path, dtype=np.uint64).reshape(-1, 2)
         want = ref.vector(vec)
+        if src.endswith("_coeffs"):
+            want = po.fft(want, inverse=True)
         same = got.shape == want.shape and np.array_equal(got, want)
         bad = None if same else (np.nonzero((got != want).any(axis=1))[0][:8] if got.shape == want.shape else "shape %s vs %s" % (got.shape, want.shape))
         print("  ", vec, "OK" if same else f"MISMATCH at {bad}")
