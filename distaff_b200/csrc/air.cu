@@ -16,6 +16,10 @@
 // Layout: the extended trace is coset-major ([column][c][k], LDE index = k*blowup + c).  Evaluation-domain step
 // s = 8k + c8 uses LDE index s*(blowup/8) => coset c = c8*(blowup/8), element k; the "next" row (LDE index + blowup) is
 // element k+1 of the same coset, so both rows are unit-stride reads across a warp.
+// The kernel is tens of thousands of straight-line instructions.  With every field multiplication inlined (42k instructions,
+// 676 KB) the warps starve on instruction fetch: ncu showed stall_no_instruction on ~50% of the samples and 38 ms at 2^20 steps.
+// Calling one shared out-of-line multiply body instead brings the same kernel to 21.6 ms (profiles/).
+#define DG_MUL_CALL 1
 #include "air.h"
 #include "air_constants.h"
 
@@ -43,6 +47,14 @@ __device__ __forceinline__ fe tw_pow(const TwiddleRef &t, unsigned long long e) 
     return fe_mul(t.lo[ee & ((1u << t.lo_bits) - 1u)], t.hi[ee >> t.lo_bits]);
 }
 
+// DG_STEP() is a block barrier every few hundred instructions: the warps of a block walk the code together, so that an instruction
+// line is fetched once per block instead of once per warp.
+#ifdef DG_AIR_NOSYNC
+#define DG_STEP()
+#else
+#define DG_STEP() __syncthreads()
+#endif
+
 template <int W>
 __device__ __forceinline__ void matvec(const fe *m, fe *s) {
     fe r[W];
@@ -52,6 +64,7 @@ __device__ __forceinline__ void matvec(const fe *m, fe *s) {
 #pragma unroll
         for (int j = 1; j < W; j++) acc = fe_add(acc, fe_mul(m[i * W + j], s[j]));
         r[i] = acc;
+        DG_STEP();
     }
 #pragma unroll
     for (int i = 0; i < W; i++) s[i] = r[i];
@@ -76,11 +89,13 @@ struct Acc {
     }
 };
 
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const AirParams P) {
+template <int BLOCK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_kernel(const AirParams P) {
     const unsigned long long n = 1ULL << P.log_n;
-    const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n * (unsigned long long)P.num_c8) return;
+    const unsigned long long total = n * (unsigned long long)P.num_c8;
+    unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = gid < total;            // no early exit: every thread takes part in the barriers
+    if (!live) gid = total - 1;
     const unsigned long long c8_local = gid >> P.log_n, k = gid & (n - 1);
     const unsigned long long c8 = c8_local + P.c8_base;
     const unsigned long long s = (k << 3) + c8;                       // evaluation-domain step
@@ -115,6 +130,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         for (int j = P.stack_depth; j < sl; j++) nw[j] = ZERO;
     }
 
+    DG_STEP();
     // ---- op flags (trace_state.rs:281-350) ----------------------------------------------------------------------------------
     const fe op_counter = cur_dec[0];
     const fe *sp = cur_dec + 1, *cf = cur_dec + 5, *ld = cur_dec + 8, *hd = cur_dec + 13;
@@ -148,6 +164,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
 
     const fe *per = P.periodic + (s & 127ULL) * 23;                   // [ark_sponge 8][masks 3][ark_hasher 12]
 
+    DG_STEP();
     // ---- decoder: op bits (decoder/op_bits.rs:10-79), constraints 0..14 -------------------------------------------------------
     {
         fe cf_sum = ZERO, ld_prod = ONE, hd_prod = ONE;
@@ -171,6 +188,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         acc.fold(14, G4, align);
     }
 
+    DG_STEP();
     // ---- decoder: sponge / flow ops (decoder/sponge.rs, flow_ops.rs) --------------------------------------------------------------
     {
         fe r_sp[4], r_img;
@@ -181,6 +199,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
             fe os[4], ns[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) os[i] = fe_cube(fe_add(sp[i], per[i]));
+            DG_STEP();
             matvec<4>(c_sponge_mds, os);
             // op_code = sum ld[i]*2^i + hd[i]*2^(5+i)
             fe opc = ld[0];
@@ -197,12 +216,14 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
 #pragma unroll
             for (int i = 0; i < 4; i++) r_sp[i] = fe_mul(f, fe_sub(os[i], ns[i]));
         }
+        DG_STEP();
         // BEGIN, LOOP, WRAP clear the sponge: flag sum * new_sponge[i]
         {
             fe fclr = fe_add(fe_add(cff[1], cff[4]), cff[5]);
 #pragma unroll
             for (int i = 0; i < 4; i++) r_sp[i] = fe_add(r_sp[i], fe_mul(fclr, nsp[i]));
         }
+        DG_STEP();
         // TEND / FEND
         {
             fe ft = cff[2], ff = cff[3], fb = fe_add(ft, ff);
@@ -222,6 +243,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         r_img = fe_mul(fe_add(cff[5], cff[6]), fe_sub(sp[0], c_loop[0]));
         acc.fold(19, G4, r_img);
 
+        DG_STEP();
         // context stack: BEGIN/LOOP push (right shift 1, slot 0 = parent hash), TEND/FEND pop (left shift 1), WRAP/BREAK/VOID copy
         {
             fe f_push = fe_add(cff[1], cff[4]), f_pop = fe_add(cff[2], cff[3]), f_copy = fe_add(fe_add(cff[5], cff[6]), cff[7]);
@@ -234,6 +256,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
                 acc.fold(20 + i, G4, v);
             }
         }
+        DG_STEP();
         // loop stack: BEGIN/TEND/FEND/WRAP/VOID copy, LOOP right shift 1 (slot 0 unconstrained), BREAK left shift 1
         {
             fe f_copy = fe_add(fe_add(fe_add(cff[1], cff[2]), fe_add(cff[3], cff[5])), cff[7]);
@@ -258,15 +281,19 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         for (int i = 0; i < 4; i++) { ldf[4 + i] = fe_mul(ldf[i], ld[2]); ldf[i] = fe_sub(ldf[i], ldf[4 + i]); }
 #pragma unroll
         for (int i = 0; i < 8; i++) { ldf[8 + i] = fe_mul(ldf[i], ld[3]); ldf[i] = fe_sub(ldf[i], ldf[8 + i]); }
+        DG_STEP();
 #pragma unroll
         for (int i = 0; i < 16; i++) { ldf[16 + i] = fe_mul(ldf[i], ld[4]); ldf[i] = fe_sub(ldf[i], ldf[16 + i]); }
+        DG_STEP();
     }
+    DG_STEP();
     fe begin_flag, noop_flag;
     {
         begin_flag = fe_mul(ldf[0], hdf_raw0);
         noop_flag = fe_mul(ldf[31], hdf[3]);
         ldf[0] = fe_mul(ldf[0], hd[0]);      // ASSERT flag adjustment
     }
+    DG_STEP();
     // ---- stack constraints (stack/mod.rs:117-195) -----------------------------------------------------------------------------------
     {
         const int base = 20 + cl + ll;       // aux constraints at base, base+1; stack slots from base+2
@@ -279,6 +306,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
                  f_roll8 = ldf[28], f_binacc = ldf[29];
         const fe f_push = hdf[0], f_cmp = hdf[1], f_rescr = hdf[2];
 
+        DG_STEP();
         // --- auxiliary constraints
         fe aux0, aux1;
         {
@@ -296,6 +324,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         acc.fold(base, G7, aux0);
         acc.fold(base + 1, G7, aux1);
 
+        DG_STEP();
         // --- per-slot shift structure.  For slot i the generic contribution of an operation is
         //        copy:         f * (o[i]   - n[i])                    when i >= from
         //        right shift s: f * (o[i-s] - n[i])                   when i >= s
@@ -347,6 +376,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
             }
             ev[i] = v;
         }
+        DG_STEP();
         // --- operation-specific constraints on the low slots
         // dup / dup2 / dup4: new[k] == old[k]
         ev[0] = fe_add(ev[0], fe_mul(fe_add(fe_add(f_dup, f_dup2), f_dup4), fe_sub(nw[0], o[0])));
@@ -358,6 +388,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         ev[1] = fe_add(ev[1], fe_mul(f_pad2, nw[1]));
         // swap: both constraints accumulate into slot 0 (stack/manipulation.rs:63-64)
         ev[0] = fe_add(ev[0], fe_mul(f_swap, fe_add(fe_sub(nw[0], o[1]), fe_sub(nw[1], o[0]))));
+        DG_STEP();
         // swap2
         ev[0] = fe_add(ev[0], fe_mul(f_swap2, fe_sub(nw[0], o[2]))); ev[1] = fe_add(ev[1], fe_mul(f_swap2, fe_sub(nw[1], o[3])));
         ev[2] = fe_add(ev[2], fe_mul(f_swap2, fe_sub(nw[2], o[0]))); ev[3] = fe_add(ev[3], fe_mul(f_swap2, fe_sub(nw[3], o[1])));
@@ -367,6 +398,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
             ev[q] = fe_add(ev[q], fe_mul(f_swap4, fe_sub(nw[q], o[4 + q])));
             ev[4 + q] = fe_add(ev[4 + q], fe_mul(f_swap4, fe_sub(nw[4 + q], o[q])));
         }
+        DG_STEP();
         // roll4 / roll8
         ev[0] = fe_add(ev[0], fe_mul(f_roll4, fe_sub(nw[0], o[3])));
 #pragma unroll
@@ -374,6 +406,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         ev[0] = fe_add(ev[0], fe_mul(f_roll8, fe_sub(nw[0], o[7])));
 #pragma unroll
         for (int q = 1; q < 8; q++) ev[q] = fe_add(ev[q], fe_mul(f_roll8, fe_sub(nw[q], o[q - 1])));
+        DG_STEP();
         // arithmetic / boolean: slot 0
         {
             fe prod = fe_mul(o[0], o[1]);
@@ -392,6 +425,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
             }
             ev[0] = fe_add(ev[0], v);
         }
+        DG_STEP();
         // choose2 / cswap2
         {
             fe c = o[4], nc = bnot(c);
@@ -402,6 +436,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
             ev[2] = fe_add(ev[2], fe_mul(f_cswap2, fe_sub(nw[2], fe_add(fe_mul(c, o[0]), fe_mul(nc, o[2])))));
             ev[3] = fe_add(ev[3], fe_mul(f_cswap2, fe_sub(nw[3], fe_add(fe_mul(c, o[1]), fe_mul(nc, o[3])))));
         }
+        DG_STEP();
         // binacc (comparison.rs:111-133)
         {
             fe bit = nw[0];
@@ -410,6 +445,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
             ev[2] = fe_add(ev[2], fe_mul(f_binacc, fe_sub(nw[2], fe_mul_small(o[2], 2))));
             ev[3] = fe_add(ev[3], fe_mul(f_binacc, fe_sub(nw[3], fe_add(o[3], fe_mul(bit, o[2])))));
         }
+        DG_STEP();
         // cmp (comparison.rs:71-108): [pow, bit_a, bit_b, not_set, gt, lt, acc_b, acc_a]
         {
             fe xb = nw[1], yb = nw[2], not_set = nw[3];
@@ -427,6 +463,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
             ev[6] = fe_add(ev[6], fe_mul(f_cmp, fe_sub(not_set, nsc)));
             ev[7] = fe_add(ev[7], fe_mul(f_cmp, fe_sub(fe_mul_small(nw[0], 2), p2)));
         }
+        DG_STEP();
         // rescr (stack/hash.rs:9-35)
         {
             fe os[6], ns[6];
@@ -444,30 +481,33 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) constraint_eval_kernel(const 
         for (int i = 0; i < P.stack_depth; i++) acc.fold(base + 2 + i, G7, ev[i]);
     }
 
+    DG_STEP();
     // ---- combine (evaluator.rs:335-358): result + sum_g adj_g * x^inc_g ------------------------------------------------------------------
     fe t_res = acc.res;
 #pragma unroll
     for (int g = 0; g < 6; g++) t_res = fe_add(t_res, fe_mul(acc.adj[g], tw_pow(P.twN, lde_index * P.inc[g])));
     // on the trace domain (except its last step) every constraint must vanish (evaluator.rs:149-158)
     if (c8 == 0 && k != n - 1) {
-        if (acc.nonzero) atomicExch(P.violation, (unsigned)(k + 1));
+        if (acc.nonzero && live) atomicExch(P.violation, (unsigned)(k + 1));
         t_res = ZERO;
     }
-    P.t_ev[out_idx] = t_res;
+    if (live) P.t_ev[out_idx] = t_res;
 }
 
 void launch_constraint_eval(Context &c, const AirParams &P) {
     air_upload_constants();
     const unsigned long long E = (unsigned long long)P.num_c8 << P.log_n;
     static int variant = -1;
-    if (variant < 0) { const char *e = getenv("DG_AIR_LB"); variant = e ? atoi(e) : 4; }   // 4 blocks/SM (128 registers, some local spills) measured fastest on B200
-    const unsigned grid = (unsigned)((E + 127) / 128);
+    if (variant < 0) { const char *e = getenv("DG_AIR_CFG"); variant = e ? atoi(e) : 1; }
+#define DG_AIR_LAUNCH(BLOCK, MINB) constraint_eval_kernel<BLOCK, MINB><<<(unsigned)((E + BLOCK - 1) / BLOCK), BLOCK, 0, c.stream>>>(P)
     switch (variant) {
-        case 2: constraint_eval_kernel<2><<<grid, 128, 0, c.stream>>>(P); break;
-        case 3: constraint_eval_kernel<3><<<grid, 128, 0, c.stream>>>(P); break;
-        case 5: constraint_eval_kernel<5><<<grid, 128, 0, c.stream>>>(P); break;
-        case 6: constraint_eval_kernel<6><<<grid, 128, 0, c.stream>>>(P); break;
-        default: constraint_eval_kernel<4><<<grid, 128, 0, c.stream>>>(P); break;
+        case 1: DG_AIR_LAUNCH(128, 4); break;
+        case 2: DG_AIR_LAUNCH(256, 2); break;
+        case 3: DG_AIR_LAUNCH(512, 1); break;
+        case 4: DG_AIR_LAUNCH(256, 1); break;
+        case 5: DG_AIR_LAUNCH(384, 1); break;
+        case 6: DG_AIR_LAUNCH(128, 3); break;
+        default: DG_AIR_LAUNCH(128, 4); break;
     }
     c.launches++;
     DG_CUDA(cudaGetLastError());

@@ -329,7 +329,13 @@ __device__ __forceinline__ fe fe_mul_v3(fe a, fe b) {
     return fe_reduce_v3(r);
 }
 // the multiply used by every kernel (tools/bench_modmul.cu: 274 G modmul/s on B200 vs 228 for v1)
+#ifdef DG_MUL_CALL
+// out-of-line variant for kernels whose fully inlined code would not fit the instruction caches
+static __device__ __noinline__ fe fe_mul_call(fe a, fe b) { return fe_mul_v3(a, b); }
+__device__ __forceinline__ fe fe_mul(fe a, fe b) { return fe_mul_call(a, b); }
+#else
 __device__ __forceinline__ fe fe_mul(fe a, fe b) { return fe_mul_v3(a, b); }
+#endif
 __device__ __forceinline__ fe fe_sqr(fe a) { return fe_mul(a, a); }
 
 // multiply by a small constant (< 2^32)

@@ -15,6 +15,9 @@
 // independent size-n transforms of the coset-scaled coefficients p[m] * w_N^(c*m); the result is stored coset-major
 // ([c][k] <-> LDE index b*k + c), which is the layout every later kernel (leaf hashing, constraint evaluation, FRI)
 // consumes with unit-stride reads.  This removes log2(b) of the log2(N) butterfly levels and all work on zeros.
+// The fully unrolled rounds are far larger than the 32 KB instruction cache; with the field multiplication out of line
+// (one shared 80-instruction body) the pass kernels shrink from 17.6k to 10k instructions and run ~4% faster (B200, 2^20 x 32 LDE).
+#define DG_MUL_CALL 1
 #include "common.cuh"
 
 namespace dg {
