@@ -5,5 +5,5 @@ Python host-side mirror of the reference interface for the prove hot path:
     distaff_b200.execute(source, inputs, ...)     <->  distaff::execute    (/root/reference/src/lib.rs:30-65), VM = host stand-in
 The compute path is hand-written CUDA behind the C-ABI of include/distaff_gpu.h; there is no CPU fallback.
 """
-from .api import (ProofOptions, StarkProof, prove, prove_device, execute, ntt, intt, lde, merkle_build, hash_rows,  # noqa: F401
+from .api import (ProofOptions, StarkProof, prove, prove_device, execute, ntt, intt, lde, merkle_build, hash_rows, hash64,  # noqa: F401
                   find_pow_nonce, field_op)

@@ -123,13 +123,29 @@ def lde(values, blowup=32):
     return out
 
 
-def merkle_build(leaves):
-    """crypto::build_merkle_nodes with blake3: bytes (n*32) -> bytes (n*32), heap layout"""
+HASH_IDS = {"blake3": 0, "rescue": 1, "poseidon": 2}
+
+
+def merkle_build(leaves, hash="blake3"):
+    """crypto::build_merkle_nodes (merkle.rs:269-294): bytes (n*32) -> bytes (n*32), heap layout; hash in blake3 | rescue | poseidon"""
     leaves = bytes(leaves)
     n = len(leaves) // 32
     out = ctypes.create_string_buffer(n * 32)
-    backend.check(backend.lib().dg_merkle_build(leaves, n, out))
+    if hash == "blake3":
+        backend.check(backend.lib().dg_merkle_build(leaves, n, out))
+    else:
+        backend.check(backend.lib().dg_merkle_build_with(HASH_IDS[hash], leaves, n, out))
     return out.raw
+
+
+def hash64(messages, hash="rescue"):
+    """crypto::hash::{blake3, rescue, poseidon} of n independent 64-byte messages: bytes (n*64) -> bytes (n*32)"""
+    messages = bytes(messages)
+    assert len(messages) % 64 == 0
+    n = len(messages) // 64
+    out = ctypes.create_string_buffer(max(1, n * 32))
+    backend.check(backend.lib().dg_hash64(HASH_IDS[hash], messages, n, out))
+    return out.raw[:n * 32]
 
 
 def hash_rows(columns):

@@ -48,6 +48,8 @@ EXPORTS = {
     "dg_lde": [vp, vp, u32, u32, u32],
     "dg_merkle_build": [vp, u64, vp],
     "dg_hash_rows": [vp, u32, u64, vp],
+    "dg_hash64": [ctypes.c_int, vp, u64, vp],
+    "dg_merkle_build_with": [ctypes.c_int, vp, u64, vp],
     "dg_find_pow_nonce": [vp, u32, ctypes.POINTER(u64), vp],
     "dg_field_op": [ctypes.c_int, ctypes.c_int, vp, vp, vp, u64],
     "dg_dev_alloc": [ctypes.POINTER(vp), ctypes.c_size_t],
@@ -58,6 +60,7 @@ EXPORTS = {
     "dg_dev_ntt": [vp, u32, u32, ctypes.c_int, fp],
     "dg_dev_lde": [vp, vp, u32, u32, u32, fp],
     "dg_dev_merkle_build": [vp, u64, vp, fp],
+    "dg_dev_merkle_build_with": [ctypes.c_int, vp, u64, vp, fp],
     "dg_dev_hash_rows": [vp, u32, u32, u32, vp, fp],
     "dg_dev_flush_l2": [],
     "dg_comm_unique_id": [vp],

@@ -4,6 +4,7 @@
 #include "prover.h"
 #include "host_fs.h"
 #include "shard.h"
+#include "poly.h"
 
 namespace dg {
 void hash_trace_rows(Context &c, const fe *ext, void *leaves, int w, int log_n, int log_blowup);
@@ -167,6 +168,16 @@ int dg_dev_merkle_build(const void *d_leaves, uint64_t n_leaves, void *d_nodes, 
         DG_CUDA(cudaStreamSynchronize(c.stream));
     });
 }
+int dg_dev_merkle_build_with(int hash, const void *d_leaves, uint64_t n_leaves, void *d_nodes, float *ms) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        EventTimer t(c.stream, ms);
+        alg_merkle_build(c, hash, d_leaves, d_nodes, n_leaves);
+        t.stop();
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
 int dg_dev_hash_rows(const void *d_ext, uint32_t width, uint32_t log_n, uint32_t log_blowup, void *d_leaves, float *ms) {
     return guarded([&] {
         Context &c = ctx();
@@ -217,6 +228,32 @@ int dg_merkle_build(const uint8_t *leaves, uint64_t n_leaves, uint8_t *nodes) {
         DevBuf d_l(n_leaves * 32), d_n(n_leaves * 32);
         DG_CUDA(cudaMemcpyAsync(d_l.p, leaves, n_leaves * 32, cudaMemcpyHostToDevice, c.stream));
         merkle_build(c, d_l.p, d_n.p, n_leaves);
+        DG_CUDA(cudaMemcpyAsync(nodes, d_n.p, n_leaves * 32, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int dg_hash64(int hash, const uint8_t *messages64, uint64_t n, uint8_t *digests32) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(hash >= 0 && hash <= 2, "hash id must be 0 (blake3), 1 (rescue) or 2 (poseidon)");
+        if (n == 0) return;
+        DG_REQUIRE(messages64 && digests32, "null buffer");
+        DevBuf d_in(n * 64), d_out(n * 32);
+        DG_CUDA(cudaMemcpyAsync(d_in.p, messages64, n * 64, cudaMemcpyHostToDevice, c.stream));
+        alg_hash64(c, hash, d_in.p, d_out.p, n);
+        DG_CUDA(cudaMemcpyAsync(digests32, d_out.p, n * 32, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    });
+}
+int dg_merkle_build_with(int hash, const uint8_t *leaves, uint64_t n_leaves, uint8_t *nodes) {
+    return guarded([&] {
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(n_leaves >= 2 && (n_leaves & (n_leaves - 1)) == 0, "number of leaves must be a power of 2 and >= 2");
+        DevBuf d_l(n_leaves * 32), d_n(n_leaves * 32);
+        DG_CUDA(cudaMemcpyAsync(d_l.p, leaves, n_leaves * 32, cudaMemcpyHostToDevice, c.stream));
+        alg_merkle_build(c, hash, d_l.p, d_n.p, n_leaves);
         DG_CUDA(cudaMemcpyAsync(nodes, d_n.p, n_leaves * 32, cudaMemcpyDeviceToHost, c.stream));
         DG_CUDA(cudaStreamSynchronize(c.stream));
     });

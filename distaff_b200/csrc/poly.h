@@ -28,6 +28,9 @@ void gather16(Context &c, const fe *src, const unsigned long long *d_idx, int co
 // ---- hashing (hash.cu) ----
 void hash_trace_rows(Context &c, const fe *ext, void *leaves, int w, int log_n, int log_blowup);
 void merkle_build(Context &c, const void *leaves, void *nodes, unsigned long long L);
+// alghash.cu: blake3 / rescue / poseidon over 64-byte messages, and Merkle trees with them
+void alg_hash64(Context &c, int hash_id, const void *in, void *out, unsigned long long n);
+void alg_merkle_build(Context &c, int hash_id, const void *leaves, void *nodes, unsigned long long L);
 void merkle_finish(Context &c, void *nodes, unsigned long long m);     // level with m nodes already at nodes[m..2m)
 unsigned long long pow_search(Context &c, const uint8_t seed[32], unsigned grinding);
 void pow_hash(const uint8_t seed[32], unsigned long long nonce, uint8_t out[32]);

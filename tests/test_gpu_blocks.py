@@ -99,6 +99,45 @@ def test_merkle_nodes_match_oracle(dg, po, log_l):
     assert dg.merkle_build(leaves) == po.merkle_nodes("blake3", leaves)
 
 
+def _le16(values):
+    return b"".join(int(v).to_bytes(16, "little") for v in values)
+
+
+def test_algebraic_hash_reference_vectors(dg):
+    """known answers of the reference's own tests (hash.rs:264-297): poseidon / rescue of [1, 2, 3, 4]"""
+    msg = _le16([1, 2, 3, 4])
+    assert list(dg.hash64(msg, "poseidon")) == [
+        224, 9, 85, 92, 75, 117, 136, 23, 142, 67, 249, 199, 39, 177, 97, 129,
+        93, 192, 153, 131, 76, 160, 94, 162, 200, 192, 187, 5, 159, 69, 48, 165]
+    assert list(dg.hash64(msg, "rescue")) == [
+        148, 191, 96, 185, 107, 196, 170, 28, 161, 214, 196, 211, 158, 111, 135, 32,
+        122, 173, 195, 37, 123, 60, 246, 104, 176, 53, 127, 67, 38, 208, 69, 54]
+
+
+@pytest.mark.parametrize("name", ["blake3", "rescue", "poseidon"])
+def test_hash64_matches_oracle(dg, po, name):
+    n = 300                                              # not a multiple of the block size
+    msgs = _rand(4 * n, 77).reshape(n, 4, 2)             # valid field elements
+    msgs[0] = 0                                          # all-zero message
+    msgs[1, :, 0] = M & 0xFFFFFFFFFFFFFFFF               # M - 1 in every lane
+    msgs[1, :, 1] = M >> 64
+    msgs[1, :, 0] -= 1
+    raw = msgs.tobytes()
+    got = dg.hash64(raw, name)
+    assert len(got) == 32 * n
+    for i in range(n):
+        assert got[32 * i:32 * i + 32] == po.hash(name, raw[64 * i:64 * i + 64]), (name, i)
+    assert dg.hash64(b"", name) == b""                   # empty batch
+
+
+@pytest.mark.parametrize("name", ["rescue", "poseidon"])
+@pytest.mark.parametrize("log_l", [1, 2, 3, 6, 9])
+def test_algebraic_merkle_nodes_match_oracle(dg, po, name, log_l):
+    n = 1 << log_l
+    leaves = _rand(2 * n, 900 + log_l).tobytes()         # leaves are digests = pairs of field elements (merkle.rs:321-338)
+    assert dg.merkle_build(leaves, name) == po.merkle_nodes(name, leaves)
+
+
 def test_pow_nonce_is_the_smallest(dg, po):
     import ctypes
     for g, seed_byte in ((0, 1), (8, 2), (12, 3), (16, 4), (20, 5)):

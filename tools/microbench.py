@@ -85,6 +85,18 @@ def main():
         for b in (polys, ext, leaves, nodes):
             b.free()
 
+    # Merkle trees with the algebraic hashes (benches/hash.rs + merkle.rs with rescue / poseidon); leaves = pairs of field elements
+    results["alg_merkle"] = []
+    for name, hid in (("rescue", 1), ("poseidon", 2)):
+        for log_l in (14, 16, 18, 20):
+            L_ = 1 << log_l
+            leaves = backend.DeviceBuffer(L_ * 32).upload(felt.random_elements(2 * L_, 7 + log_l))
+            nodes = backend.DeviceBuffer(L_ * 32)
+            med, best = timed(lambda ms: backend.check(L.dg_dev_merkle_build_with(hid, leaves.ptr, L_, nodes.ptr, ms)), max(3, args.iters // 2))
+            results["alg_merkle"].append({"hash": name, "log_leaves": log_l, "ms": med, "hashes_per_s": (L_ - 1) / (med * 1e-3)})
+            print(f"{name:8s} merkle 2^{log_l} leaves: {med:8.3f} ms  {(L_ - 1) / (med * 1e-3) / 1e6:8.2f} M hashes/s", flush=True)
+            leaves.free(); nodes.free()
+
     if args.out:
         os.makedirs(os.path.dirname(args.out), exist_ok=True)
         json.dump(results, open(args.out, "w"), indent=1)
