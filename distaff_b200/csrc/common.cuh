@@ -126,6 +126,7 @@ struct Context {
     TwiddleRef twiddle(int log_order, bool inverse);
     std::map<int, DevBuf> single_tables;    // full power tables w^e, e < 2^log_order (small orders only)
     const fe *single_table(int log_order);
+    std::map<long long, DevBuf> lde_twiddles;   // per (log_n, log_blowup, first pass size): merged lane/coset twiddles of the LDE's first pass (ntt.cu)
     const fe *roots(int log_l, bool inverse) const { return small_roots[inverse ? 1 : 0].as<fe>() + small_root_offset[log_l]; }
 };
 

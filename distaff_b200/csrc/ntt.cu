@@ -40,6 +40,8 @@ struct PassGeom {
     int coset_fast;                     // fold == 1: input factor from a single-level table, lane factor merged into the output twiddle
     const fe *cw_point;                 // cw_point[e] = (w_N^in_point)^e, e < cw_point_mask + 1
     unsigned cw_point_mask;
+    const fe *tw_full;                  // coset_fast: tw_full[coset][k * out_point + lane] = cw^(lane * (k * blowup + coset)), or null
+    long long tw_full_stride;           // elements per coset (= transform size n)
     int log_blowup;
     unsigned coset0;                    // first coset handled by this launch (blockIdx.y = coset - coset0)
     const fe *roots;                    // per-stage twiddle tables of the L-point transform: W_st[j] = w_L^(j << st), back to back
@@ -127,13 +129,12 @@ __device__ __forceinline__ void ntt_round(const fe *__restrict__ src, fe *__rest
                     // p[j] * w_N^(c*pos*in_point); the lane part w_N^(c*lane) rides on the output twiddle
                     x[m] = fe_mul(src[j], g.cw_point[((g.coset0 + (unsigned)blockIdx.y) * (unsigned)pos) & g.cw_point_mask]);
                 } else if (g.coset_on) {
+                    // sum_f src[j + f n] w_N^(c (j + f n)) = w_N^(c j) * Horner_f(src[j + f n]; u),  u = w_N^(c n) (constant per coset)
                     const unsigned long long c = g.coset0 + blockIdx.y;
-                    fe v = fe_make(0, 0);
-                    for (int f = 0; f < g.fold; f++) {
-                        const long long jj = j + (long long)f * g.fold_stride;
-                        v = fe_add(v, fe_mul(src[jj], tw_lookup(g.cw, c * (unsigned long long)jj)));
-                    }
-                    x[m] = v;
+                    const fe u = tw_lookup(g.cw, c * (unsigned long long)g.fold_stride);
+                    fe v = src[j + (long long)(g.fold - 1) * g.fold_stride];
+                    for (int f = g.fold - 2; f >= 0; f--) v = fe_add(fe_mul(v, u), src[j + (long long)f * g.fold_stride]);
+                    x[m] = fe_mul(v, tw_lookup(g.cw, c * (unsigned long long)j));
                 } else {
                     x[m] = src[j];
                 }
@@ -148,7 +149,12 @@ __device__ __forceinline__ void ntt_round(const fe *__restrict__ src, fe *__rest
             if (LAST) {                        // position q holds X[bitrev(q)]
                 const unsigned k = __brev((unsigned)pos) >> (32 - LOG_L);
                 fe v = x[m];
-                if (g.coset_fast && g.tw_on) v = fe_mul(v, tw_lookup(g.cw, (unsigned long long)(tile * T + t) * (((unsigned long long)k << g.log_blowup) + g.coset0 + blockIdx.y)));
+                if (g.coset_fast && g.tw_on) {
+                    if (g.tw_full)          // streamed table in the layout of the output: one 16-byte load instead of two loads and a multiplication
+                        v = fe_mul(v, g.tw_full[(long long)(g.coset0 + blockIdx.y) * g.tw_full_stride + (long long)(tile * T + t) * g.out_lane + (long long)k * g.out_point]);
+                    else
+                        v = fe_mul(v, tw_lookup(g.cw, (unsigned long long)(tile * T + t) * (((unsigned long long)k << g.log_blowup) + g.coset0 + blockIdx.y)));
+                }
                 else if (g.tw_on) v = fe_mul(v, tw_lookup(g.tw, (unsigned long long)(tile * T + t) * k));
                 if (g.has_scale) v = fe_mul(v, g.scale);
                 dst[(long long)t * g.out_lane + (long long)k * g.out_point] = v;
@@ -232,6 +238,34 @@ static int split_passes(int log_n, int l[3]) {
 
 struct CosetSpec { bool on; int log_blowup; int fold; unsigned coset0; };
 
+// table[c][k * R1 + lane] = w_N^(lane * (k * b + c)): the twiddle the first LDE pass applies to output k of lane `lane` on coset c.
+// It depends on the shape only (n, b, first pass size), so it is built once per shape and kept: N elements (512 MB for 2^20 x 32).
+__global__ void lde_twiddle_fill_kernel(fe *table, TwiddleRef cw, int log_n, int log_r1, int log_b) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >> (log_n + log_b)) return;
+    const unsigned long long c = i >> log_n, pos = i & ((1ULL << log_n) - 1);
+    const unsigned long long lane = pos & ((1ULL << log_r1) - 1), k = pos >> log_r1;
+    table[i] = tw_lookup(cw, lane * ((k << log_b) + c));
+}
+static const fe *lde_twiddle_table(Context &c, int log_n, int log_b, int l0) {
+    static long long cap = -1;
+    if (cap < 0) { const char *e = getenv("DG_LDE_TW_MB"); cap = (e ? atoll(e) : 1024) << 20; }    // 0 disables the table
+    const size_t bytes = ((size_t)16 << (log_n + log_b));
+    if ((long long)bytes > cap) return nullptr;
+    const long long key = ((long long)log_n << 16) | (log_b << 8) | l0;
+    auto it = c.lde_twiddles.find(key);
+    if (it == c.lde_twiddles.end()) {
+        DevBuf t;
+        t.alloc(bytes, true);
+        const unsigned long long cnt = 1ULL << (log_n + log_b);
+        lde_twiddle_fill_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, c.stream>>>(t.as<fe>(), c.twiddle(log_n + log_b, false), log_n, log_n - l0, log_b);
+        c.launches++;
+        DG_CUDA(cudaGetLastError());
+        it = c.lde_twiddles.emplace(key, std::move(t)).first;
+    }
+    return it->second.as<fe>();
+}
+
 // Runs the passes of one batched transform.  `by` = number of y-batches (cosets for the LDE, else 1), `bz` = vectors.
 // src strides: vector stride src_stride (z), y stride 0 for the LDE (every coset reads the same coefficients).
 static void run_transform(Context &c, const fe *src, fe *dst, int log_n, bool inverse, unsigned by, unsigned bz, long long src_stride_z,
@@ -289,6 +323,7 @@ static void run_transform(Context &c, const fe *src, fe *dst, int log_n, bool in
         g.in_batch_y = 0; g.in_batch_z = src_stride_z; g.out_batch_y = tmp_stride_y; g.out_batch_z = tmp_stride_z;
         g.lane_major = 0;
         g.tw_on = 1; g.tw = c.twiddle(log_n, inverse);
+        if (g.coset_fast) { g.tw_full = lde_twiddle_table(c, log_n, cs.log_blowup, l[0]); g.tw_full_stride = n; }
         g.roots = c.roots(l[0], inverse);
         launch_pass(c, l[0], g, src, tmp, g.num_tiles, by, bz);
     }
