@@ -64,9 +64,9 @@ __global__ void field_op_kernel(int op, int impl, const fe *a, const fe *b, fe *
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fe x = a[i], y = b ? b[i] : fe_make(0, 0), r;
-    if (impl == 2 && op == 2) {
+    if ((impl == 2 || impl == 3) && op == 2) {
 #ifdef __CUDA_ARCH__
-        r = ptx::fe_mul_v1(x, y);
+        r = impl == 2 ? ptx::fe_mul_v1(x, y) : ptx::fe_mul_v3(x, y);      // earlier multiplies, kept for differential tests
 #endif
     } else if (impl == 0) {
         switch (op) {

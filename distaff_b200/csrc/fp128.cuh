@@ -88,6 +88,50 @@ __host__ __device__ inline fe fe_inv(fe a) { return fe_pow_u128(a, DG_M_LO - 2UL
 #ifdef __CUDA_ARCH__
 namespace ptx {
 
+// fe_add: select-based (13 ALU instructions).  A mask-based variant with an out-of-line path for sums in [M, 2^128) is two
+// instructions shorter but puts a call site into every addition; measured slower inside the NTT / constraint kernels (DG_ADD_V2).
+#ifdef DG_ADD_V2
+// a + b: add, then add C back when the sum overflowed 2^128 (the wrapped value + C is the canonical result).  Without an overflow the
+// sum is canonical unless it lies in [M, 2^128), which needs an all-ones top limb: that case goes to an out-of-line slow path.
+static __device__ __noinline__ fe fe_add_slow(unsigned int s0, unsigned int s1, unsigned int s2, unsigned int s3) {
+    // s >= 2^128 - 2^96: subtract M if s >= M  (s - M = s + C - 2^128)
+    unsigned int q0, q1, q2, q3, g;
+    asm("add.cc.u32  %0, %5, 0xffffffff;\n\t"
+        "addc.cc.u32 %1, %6, 0x00002cff;\n\t"
+        "addc.cc.u32 %2, %7, 0;\n\t"
+        "addc.cc.u32 %3, %8, 0;\n\t"
+        "addc.u32    %4, 0, 0;"
+        : "=&r"(q0), "=&r"(q1), "=&r"(q2), "=&r"(q3), "=&r"(g) : "r"(s0), "r"(s1), "r"(s2), "r"(s3));
+    fe out;
+    out.lo = ((unsigned long long)(g ? q1 : s1) << 32) | (g ? q0 : s0);
+    out.hi = ((unsigned long long)(g ? q3 : s3) << 32) | (g ? q2 : s2);
+    return out;
+}
+__device__ __forceinline__ fe fe_add(fe a, fe b) {
+    unsigned int s0, s1, s2, s3, m, c1;
+    (void)c1;
+    asm("add.cc.u32  %0, %6, %10;\n\t"
+        "addc.cc.u32 %1, %7, %11;\n\t"
+        "addc.cc.u32 %2, %8, %12;\n\t"
+        "addc.cc.u32 %3, %9, %13;\n\t"
+        "addc.u32    %5, 0, 0;\n\t"            // carry out of 2^128 (a subc here would read the flag with the borrow convention)
+        "mul.lo.u32  %4, %5, 0xffffffff;\n\t"  // m = 0xffffffff on overflow, else 0  (multiplies: FMA pipe)
+        "mul.lo.u32  %5, %5, 0x00002cff;\n\t"
+        "add.cc.u32  %0, %0, %4;\n\t"          // + (C & mask): C = 0x2cff_ffffffff
+        "addc.cc.u32 %1, %1, %5;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.u32    %3, %3, 0;"
+        : "=&r"(s0), "=&r"(s1), "=&r"(s2), "=&r"(s3), "=&r"(m), "=&r"(c1)
+        : "r"((unsigned int)a.lo), "r"((unsigned int)(a.lo >> 32)), "r"((unsigned int)a.hi), "r"((unsigned int)(a.hi >> 32)),
+          "r"((unsigned int)b.lo), "r"((unsigned int)(b.lo >> 32)), "r"((unsigned int)b.hi), "r"((unsigned int)(b.hi >> 32)));
+    if (__builtin_expect((s3 == 0xffffffffu) & (m == 0u), 0)) return fe_add_slow(s0, s1, s2, s3);
+    fe r;
+    r.lo = ((unsigned long long)s1 << 32) | s0;
+    r.hi = ((unsigned long long)s3 << 32) | s2;
+    return r;
+}
+
+#else
 __device__ __forceinline__ fe fe_add(fe a, fe b) {
     unsigned long long s0, s1, t0, t1;
     unsigned int c1, c2;
@@ -106,6 +150,32 @@ __device__ __forceinline__ fe fe_add(fe a, fe b) {
     return r;
 }
 
+#endif
+
+#ifndef DG_SUB_V1
+// a - b: subtract, then subtract C when the difference borrowed (a - b + M = a - b - C mod 2^128); always canonical
+__device__ __forceinline__ fe fe_sub(fe a, fe b) {
+    unsigned int d0, d1, d2, d3, m, c1;
+    (void)m; (void)c1;
+    asm("sub.cc.u32  %0, %6, %10;\n\t"
+        "subc.cc.u32 %1, %7, %11;\n\t"
+        "subc.cc.u32 %2, %8, %12;\n\t"
+        "subc.cc.u32 %3, %9, %13;\n\t"
+        "subc.u32    %4, 0, 0;\n\t"            // m = 0xffffffff on borrow, else 0
+        "and.b32     %5, %4, 0x00002cff;\n\t"
+        "sub.cc.u32  %0, %0, %4;\n\t"
+        "subc.cc.u32 %1, %1, %5;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.u32    %3, %3, 0;"
+        : "=&r"(d0), "=&r"(d1), "=&r"(d2), "=&r"(d3), "=&r"(m), "=&r"(c1)
+        : "r"((unsigned int)a.lo), "r"((unsigned int)(a.lo >> 32)), "r"((unsigned int)a.hi), "r"((unsigned int)(a.hi >> 32)),
+          "r"((unsigned int)b.lo), "r"((unsigned int)(b.lo >> 32)), "r"((unsigned int)b.hi), "r"((unsigned int)(b.hi >> 32)));
+    fe r;
+    r.lo = ((unsigned long long)d1 << 32) | d0;
+    r.hi = ((unsigned long long)d3 << 32) | d2;
+    return r;
+}
+#else
 __device__ __forceinline__ fe fe_sub(fe a, fe b) {
     unsigned long long d0, d1, t0, t1;
     unsigned int bw;
@@ -121,6 +191,8 @@ __device__ __forceinline__ fe fe_sub(fe a, fe b) {
     fe r; r.lo = bw ? t0 : d0; r.hi = bw ? t1 : d1;   // a - b + M == a - b - C (mod 2^128)
     return r;
 }
+
+#endif
 
 __device__ __forceinline__ fe fe_neg(fe a) { return fe_sub(fe_make(0, 0), a); }
 
@@ -328,13 +400,99 @@ __device__ __forceinline__ fe fe_mul_v3(fe a, fe b) {
     mul_wide_eo(x, y, r);
     return fe_reduce_v3(r);
 }
-// the multiply used by every kernel (tools/bench_modmul.cu: 274 G modmul/s on B200 vs 228 for v1)
+// ---- variant 4: v3 with less work on the arithmetic pipe ---------------------------------------------------------------------------
+// On B200 the ALU pipe (IADD3 / SEL / LOP3) is what the NTT and constraint kernels saturate (ncu: ALU 61-66 % busy, FMA pipe 27-29 %).
+//   * the second fold adds (T*K) << 32 through a multiply-add chain instead of an add-with-carry sequence;
+//   * the result needs the final "subtract M" only if it overflowed 2^128 or its top limb is all ones (probability ~2^-32 for
+//     uniform values), so that case is an out-of-line slow path behind one predicate: 31 ALU instructions per product instead of 40.
+// (Keeping the "x*1 + c" limb additions on the FMA pipe with an opaque multiplier was tried: ptxas splits them into IMAD + IADD3.)
+#define DG_HAVE_V4 1
+static __device__ __forceinline__ fe fe_canon_inline(unsigned int v0, unsigned int v1, unsigned int v2, unsigned int v3, unsigned int cy);
+static __device__ __noinline__ fe fe_canon_slow(unsigned int v0, unsigned int v1, unsigned int v2, unsigned int v3, unsigned int cy) {
+    unsigned int q0, q1, q2, q3, g;
+    asm("add.cc.u32  %0, %5, 0xffffffff;\n\t"
+        "addc.cc.u32 %1, %6, 0x00002cff;\n\t"
+        "addc.cc.u32 %2, %7, 0;\n\t"
+        "addc.cc.u32 %3, %8, 0;\n\t"
+        "addc.u32    %4, 0, 0;"
+        : "=&r"(q0), "=&r"(q1), "=&r"(q2), "=&r"(q3), "=&r"(g) : "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+    const bool use_q = (cy | g) != 0;
+    fe out;
+    out.lo = ((unsigned long long)(use_q ? q1 : v1) << 32) | (use_q ? q0 : v0);
+    out.hi = ((unsigned long long)(use_q ? q3 : v3) << 32) | (use_q ? q2 : v2);
+    return out;
+}
+template <bool NESTED_CALL>
+__device__ __forceinline__ fe fe_reduce_v4(const unsigned int r[8]) {
+    const unsigned int K = 11520u;   // 45 * 2^8 : C = K * 2^32 - 1
+    const unsigned int one = 1u;
+    // V = lo + ((hi * K) << 32)   (6 limbs), all on multiply-add chains
+    unsigned long long t0 = wmad(r[4], K, (unsigned long long)r[1]);
+    unsigned long long t1 = wmad(r[2], one, wmad(r[5], K, t0 >> 32));
+    unsigned long long t2 = wmad(r[3], one, wmad(r[6], K, t1 >> 32));
+    unsigned long long t3 = wmad(r[7], K, t2 >> 32);
+    unsigned int v0 = r[0], v1 = (unsigned int)t0, v2 = (unsigned int)t1, v3 = (unsigned int)t2, v4 = (unsigned int)t3, v5 = (unsigned int)(t3 >> 32);
+    // V -= hi
+    asm("sub.cc.u32  %0, %0, %6;\n\t"
+        "subc.cc.u32 %1, %1, %7;\n\t"
+        "subc.cc.u32 %2, %2, %8;\n\t"
+        "subc.cc.u32 %3, %3, %9;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t"
+        "subc.u32    %5, %5, 0;"
+        : "+r"(v0), "+r"(v1), "+r"(v2), "+r"(v3), "+r"(v4), "+r"(v5) : "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+    // fold the 47-bit top T = v5:v4 :  + (T*K) << 32 on a multiply-add chain (T*K < 2^61), then - T
+    unsigned long long u1 = wmad(v4, K, (unsigned long long)v1);
+    unsigned long long u2 = wmad(v2, one, wmad(v5, K, u1 >> 32));
+    unsigned long long u3 = wmad(v3, one, u2 >> 32);
+    v1 = (unsigned int)u1; v2 = (unsigned int)u2; v3 = (unsigned int)u3;
+    unsigned int cy = (unsigned int)(u3 >> 32);
+    asm("sub.cc.u32  %0, %0, %5;\n\t"
+        "subc.cc.u32 %1, %1, %6;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.u32    %4, %4, 0;"
+        : "+r"(v0), "+r"(v1), "+r"(v2), "+r"(v3), "+r"(cy) : "r"(v4), "r"(v5));
+    // cy is now carry - borrow in {0, 1}: the value is non-negative and < 2^128 + 2^93.  It is canonical unless it overflowed or
+    // lies in [2^128 - 2^96, 2^128)
+    if (__builtin_expect((cy != 0u) | (v3 == 0xffffffffu), 0)) {
+        if (NESTED_CALL) return fe_canon_slow(v0, v1, v2, v3, cy);
+        return fe_canon_inline(v0, v1, v2, v3, cy);        // inside an out-of-line multiply: a plain branch, no nested call frame
+    }
+    fe out;
+    out.lo = ((unsigned long long)v1 << 32) | v0;
+    out.hi = ((unsigned long long)v3 << 32) | v2;
+    return out;
+}
+static __device__ __forceinline__ fe fe_canon_inline(unsigned int v0, unsigned int v1, unsigned int v2, unsigned int v3, unsigned int cy) {
+    unsigned int q0, q1, q2, q3, g;
+    asm volatile("add.cc.u32  %0, %5, 0xffffffff;\n\t"
+        "addc.cc.u32 %1, %6, 0x00002cff;\n\t"
+        "addc.cc.u32 %2, %7, 0;\n\t"
+        "addc.cc.u32 %3, %8, 0;\n\t"
+        "addc.u32    %4, 0, 0;"
+        : "=&r"(q0), "=&r"(q1), "=&r"(q2), "=&r"(q3), "=&r"(g) : "r"(v0), "r"(v1), "r"(v2), "r"(v3));
+    const bool use_q = (cy | g) != 0;
+    fe out;
+    out.lo = ((unsigned long long)(use_q ? q1 : v1) << 32) | (use_q ? q0 : v0);
+    out.hi = ((unsigned long long)(use_q ? q3 : v3) << 32) | (use_q ? q2 : v2);
+    return out;
+}
+template <bool NESTED_CALL>
+__device__ __forceinline__ fe fe_mul_v4t(fe a, fe b) {
+    unsigned int x[4] = { (unsigned int)a.lo, (unsigned int)(a.lo >> 32), (unsigned int)a.hi, (unsigned int)(a.hi >> 32) };
+    unsigned int y[4] = { (unsigned int)b.lo, (unsigned int)(b.lo >> 32), (unsigned int)b.hi, (unsigned int)(b.hi >> 32) };
+    unsigned int r[8];
+    mul_wide_eo(x, y, r);
+    return fe_reduce_v4<NESTED_CALL>(r);
+}
+__device__ __forceinline__ fe fe_mul_v4(fe a, fe b) { return fe_mul_v4t<true>(a, b); }
+// the multiply used by every kernel (tools/bench_modmul.cu on B200: v1 228, v3 274, v4 292 G modmul/s; butterfly mix 183 / 199 / 224 G/s)
 #ifdef DG_MUL_CALL
 // out-of-line variant for kernels whose fully inlined code would not fit the instruction caches
-static __device__ __noinline__ fe fe_mul_call(fe a, fe b) { return fe_mul_v3(a, b); }
+static __device__ __noinline__ fe fe_mul_call(fe a, fe b) { return fe_mul_v4t<false>(a, b); }
 __device__ __forceinline__ fe fe_mul(fe a, fe b) { return fe_mul_call(a, b); }
 #else
-__device__ __forceinline__ fe fe_mul(fe a, fe b) { return fe_mul_v3(a, b); }
+__device__ __forceinline__ fe fe_mul(fe a, fe b) { return fe_mul_v4(a, b); }
 #endif
 __device__ __forceinline__ fe fe_sqr(fe a) { return fe_mul(a, a); }
 

@@ -96,7 +96,7 @@ int dg_find_pow_nonce(const uint8_t seed[32], uint32_t grinding_factor, uint64_t
 int dg_hash64(int hash, const uint8_t *messages64, uint64_t n, uint8_t *digests32);
 int dg_merkle_build_with(int hash, const uint8_t *leaves, uint64_t n_leaves, uint8_t *nodes);
 /* element-wise field ops on vectors (op: 0 add, 1 sub, 2 mul, 3 inv, 4 exp(a, b)), for differential tests of the arithmetic;
- * impl: 0 = PTX path used by the kernels, 1 = portable C++ path */
+ * impl: 0 = PTX path used by the kernels, 1 = portable C++ path, 2 / 3 = earlier PTX multiplies (op 2 only) */
 int dg_field_op(int op, int impl, const uint8_t *a, const uint8_t *b, uint8_t *out, uint64_t n);
 
 /* ---- device-resident variants (timed with CUDA events on the library's stream; *ms may be NULL) ----------------------- */

@@ -45,6 +45,29 @@ def test_field_ops_ptx_and_portable_match_oracle(dg, po):
         assert po.field_op("mul", x, y) == x * y % M
 
 
+def test_mul_crafted_reduction_paths(dg):
+    """operand pairs whose product is congruent to a tiny residue: the Solinas fold overflows 2^128 / ends with an all-ones top limb,
+    paths random operands reach with probability ~2^-35 (tools/gen_mul_vectors.py); checked against Python integers for every multiply"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gen_mul_vectors
+    from distaff_b200 import felt
+    pairs = gen_mul_vectors.pairs()
+    a = felt.from_ints([p[0] for p in pairs])
+    b = felt.from_ints([p[1] for p in pairs])
+    want = [(x * y) % M for x, y in pairs]
+    for impl in (0, 1, 2, 3):
+        assert felt.to_ints(dg.field_op("mul", a, b, impl=impl)) == want, impl
+    # sums in [M, 2^128) (all-ones top limb without overflow) and differences that borrow
+    near = [M - 1, M - 2, M - 2**32, M - 2**64, M - 2**96, 2**128 - 2**96 - 1 - (2**128 - M), 2**127, 2**127 - 1, 1, 2, 2**96, 2**96 - 1, 45 * 2**40, 45 * 2**40 - 1]
+    xs = [x % M for x in near for _ in near]
+    ys = [y % M for _ in near for y in near]
+    fa, fb = felt.from_ints(xs), felt.from_ints(ys)
+    for impl in (0, 1):
+        assert felt.to_ints(dg.field_op("add", fa, fb, impl=impl)) == [(x + y) % M for x, y in zip(xs, ys)], impl
+        assert felt.to_ints(dg.field_op("sub", fa, fb, impl=impl)) == [(x - y) % M for x, y in zip(xs, ys)], impl
+
+
 @pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 8, 10, 11, 12, 13, 16, 19, 20, 21, 22])
 def test_ntt_matches_oracle(dg, po, log_n):
     n = 1 << log_n

@@ -11,6 +11,7 @@ template <int V> __device__ __forceinline__ fe mulv(fe a, fe b) {
 #ifdef __CUDA_ARCH__
     if (V == 1) return ptx::fe_mul_v1(a, b);
     if (V == 2) return ptx::fe_mul_v3(a, b);
+    if (V == 3) return ptx::fe_mul_v4(a, b);
 #endif
     return portable::fe_mul(a, b);
 }
@@ -62,6 +63,11 @@ int main() {
     std::vector<fe> ea, eb;
     for (int i = 0; i < ne; i++) for (int j = 0; j < ne; j++) { ea.push_back(edge[i]); eb.push_back(edge[j]); }
     for (int i = 0; i < 200000; i++) { ea.push_back(h[i % n]); eb.push_back(h[(i * 7 + 3) % n]); }
+    {   // crafted pairs (tools/gen_mul_vectors.py): products whose partially reduced value overflows 2^128 / has an all-ones top limb
+        FILE *f = fopen("tools/_bin/mul_vectors.bin", "rb");
+        if (f) { fe ab[2]; int cnt = 0; while (fread(ab, 16, 2, f) == 2) { ea.push_back(ab[0]); eb.push_back(ab[1]); cnt++; } fclose(f); printf("%d crafted pairs\n", cnt); }
+        else printf("tools/_bin/mul_vectors.bin not found: crafted pairs skipped\n");
+    }
     fe *d_in, *d_out, *da, *db, *d0, *d1;
     cudaMalloc(&d_in, n * 16); cudaMalloc(&d_out, n * 16);
     cudaMemcpy(d_in, h.data(), n * 16, cudaMemcpyHostToDevice);
@@ -75,11 +81,13 @@ int main() {
 #ifdef DG_HAVE_V3
     check<2><<<(m + 255) / 256, 256>>>(da, db, d1, m); cmp("v3");
 #endif
+    check<3><<<(m + 255) / 256, 256>>>(da, db, d1, m); cmp("v4");
     run<0>("portable", d_in, d_out, blocks, iters);
     run<1>("ptx", d_in, d_out, blocks, iters);
 #ifdef DG_HAVE_V3
     run<2>("v3", d_in, d_out, blocks, iters);
 #endif
+    run<3>("v4", d_in, d_out, blocks, iters);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
