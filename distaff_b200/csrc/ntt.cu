@@ -179,6 +179,12 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const fe *__restrict__
     dst += (long long)blockIdx.y * g.out_batch_y + (long long)blockIdx.z * g.out_batch_z + (long long)outer * g.out_outer +
            (long long)tile * T * g.out_lane;
     for (int i = threadIdx.x; i < L - 1; i += blockDim.x) s_tw[i] = g.roots[i];
+    if (g.tw_full) {
+        // the streamed twiddles are consumed in the last round: start pulling this block's T*16-byte segments (one per output k) into L2 now
+        const fe *tb = g.tw_full + (long long)(g.coset0 + blockIdx.y) * g.tw_full_stride + (long long)tile * T * g.out_lane;
+        for (int k = threadIdx.x; k < L; k += blockDim.x)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(tb + (long long)k * g.out_point));
+    }
     __syncthreads();
     ntt_round<LOG_L, 0, RD::R1, true, RD::R2 == 0, LANE_MAJOR>(src, dst, s_data, s_tw, g, tile, in_base);
     if constexpr (RD::R2 > 0) {
