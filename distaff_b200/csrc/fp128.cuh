@@ -89,49 +89,7 @@ __host__ __device__ inline fe fe_inv(fe a) { return fe_pow_u128(a, DG_M_LO - 2UL
 namespace ptx {
 
 // fe_add: select-based (13 ALU instructions).  A mask-based variant with an out-of-line path for sums in [M, 2^128) is two
-// instructions shorter but puts a call site into every addition; measured slower inside the NTT / constraint kernels (DG_ADD_V2).
-#ifdef DG_ADD_V2
-// a + b: add, then add C back when the sum overflowed 2^128 (the wrapped value + C is the canonical result).  Without an overflow the
-// sum is canonical unless it lies in [M, 2^128), which needs an all-ones top limb: that case goes to an out-of-line slow path.
-static __device__ __noinline__ fe fe_add_slow(unsigned int s0, unsigned int s1, unsigned int s2, unsigned int s3) {
-    // s >= 2^128 - 2^96: subtract M if s >= M  (s - M = s + C - 2^128)
-    unsigned int q0, q1, q2, q3, g;
-    asm("add.cc.u32  %0, %5, 0xffffffff;\n\t"
-        "addc.cc.u32 %1, %6, 0x00002cff;\n\t"
-        "addc.cc.u32 %2, %7, 0;\n\t"
-        "addc.cc.u32 %3, %8, 0;\n\t"
-        "addc.u32    %4, 0, 0;"
-        : "=&r"(q0), "=&r"(q1), "=&r"(q2), "=&r"(q3), "=&r"(g) : "r"(s0), "r"(s1), "r"(s2), "r"(s3));
-    fe out;
-    out.lo = ((unsigned long long)(g ? q1 : s1) << 32) | (g ? q0 : s0);
-    out.hi = ((unsigned long long)(g ? q3 : s3) << 32) | (g ? q2 : s2);
-    return out;
-}
-__device__ __forceinline__ fe fe_add(fe a, fe b) {
-    unsigned int s0, s1, s2, s3, m, c1;
-    (void)c1;
-    asm("add.cc.u32  %0, %6, %10;\n\t"
-        "addc.cc.u32 %1, %7, %11;\n\t"
-        "addc.cc.u32 %2, %8, %12;\n\t"
-        "addc.cc.u32 %3, %9, %13;\n\t"
-        "addc.u32    %5, 0, 0;\n\t"            // carry out of 2^128 (a subc here would read the flag with the borrow convention)
-        "mul.lo.u32  %4, %5, 0xffffffff;\n\t"  // m = 0xffffffff on overflow, else 0  (multiplies: FMA pipe)
-        "mul.lo.u32  %5, %5, 0x00002cff;\n\t"
-        "add.cc.u32  %0, %0, %4;\n\t"          // + (C & mask): C = 0x2cff_ffffffff
-        "addc.cc.u32 %1, %1, %5;\n\t"
-        "addc.cc.u32 %2, %2, 0;\n\t"
-        "addc.u32    %3, %3, 0;"
-        : "=&r"(s0), "=&r"(s1), "=&r"(s2), "=&r"(s3), "=&r"(m), "=&r"(c1)
-        : "r"((unsigned int)a.lo), "r"((unsigned int)(a.lo >> 32)), "r"((unsigned int)a.hi), "r"((unsigned int)(a.hi >> 32)),
-          "r"((unsigned int)b.lo), "r"((unsigned int)(b.lo >> 32)), "r"((unsigned int)b.hi), "r"((unsigned int)(b.hi >> 32)));
-    if (__builtin_expect((s3 == 0xffffffffu) & (m == 0u), 0)) return fe_add_slow(s0, s1, s2, s3);
-    fe r;
-    r.lo = ((unsigned long long)s1 << 32) | s0;
-    r.hi = ((unsigned long long)s3 << 32) | s2;
-    return r;
-}
-
-#else
+// instructions shorter but puts a call site into every addition: measured slower inside the NTT / constraint kernels, removed.
 __device__ __forceinline__ fe fe_add(fe a, fe b) {
     unsigned long long s0, s1, t0, t1;
     unsigned int c1, c2;
@@ -150,7 +108,6 @@ __device__ __forceinline__ fe fe_add(fe a, fe b) {
     return r;
 }
 
-#endif
 
 #ifndef DG_SUB_V1
 // a - b: subtract, then subtract C when the difference borrowed (a - b + M = a - b - C mod 2^128); always canonical

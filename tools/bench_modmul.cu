@@ -34,6 +34,58 @@ __global__ void __launch_bounds__(256) tput_bfly(const fe *in, fe *out, int iter
     }
     out[i] = fe_add(fe_add(a, b), fe_add(c, d));
 }
+// ---- call-structure experiment at the occupancy of the real kernels (16 warps/SM): 4 independent butterflies per iteration with
+//      (0) inlined multiplies, (1) one out-of-line multiply per butterfly, (2) one out-of-line call per PAIR of multiplies
+struct fe2 { fe a, b; };
+#ifdef __CUDA_ARCH__
+static __device__ __noinline__ fe mul1_call(fe a, fe b) { return ptx::fe_mul_v4t<false>(a, b); }
+static __device__ __noinline__ fe2 mul2_call(fe a0, fe b0, fe a1, fe b1) { fe2 r; r.a = ptx::fe_mul_v4t<false>(a0, b0); r.b = ptx::fe_mul_v4t<false>(a1, b1); return r; }
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) tput_call(const fe *in, fe *out, int iters) {
+    extern __shared__ unsigned char pad[];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    fe x[8], w = in[i + 8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) x[q] = in[i + q];
+    if (iters < 0) pad[threadIdx.x] = 1;
+#ifdef __CUDA_ARCH__
+    for (int k = 0; k < iters; k++) {
+        fe d[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { fe a = x[2 * q], b = x[2 * q + 1]; x[2 * q] = fe_add(a, b); d[q] = fe_sub(a, b); }
+        if (MODE == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) x[2 * q + 1] = ptx::fe_mul_v4(d[q], w);
+        } else if (MODE == 1) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) x[2 * q + 1] = mul1_call(d[q], w);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q += 2) { fe2 r = mul2_call(d[q], w, d[q + 1], w); x[2 * q + 1] = r.a; x[2 * q + 3] = r.b; }
+        }
+        // rotate so that the chains mix
+        fe t = x[1]; x[1] = x[3]; x[3] = x[5]; x[5] = x[7]; x[7] = t;
+    }
+#endif
+    fe s = x[0];
+#pragma unroll
+    for (int q = 1; q < 8; q++) s = fe_add(s, x[q]);
+    out[i] = s;
+}
+template <int MODE> void run_call(const char *name, fe *d_in, fe *d_out, int blocks, int iters) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaFuncSetAttribute(tput_call<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    float best = 1e9;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        tput_call<MODE><<<blocks, 256, 100 * 1024>>>(d_in, d_out, iters);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    printf("%-22s %8.3f ms  %7.1f Gbfly/s (16 warps/SM)\n", name, best, (double)blocks * 256 * iters * 4 / best / 1e6);
+}
+
 template <int V> __global__ void check(const fe *a, const fe *b, fe *o, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) o[i] = mulv<V>(a[i], b[i]); }
 
 template <int V> void run(const char *name, fe *d_in, fe *d_out, int blocks, int iters) {
@@ -52,7 +104,7 @@ template <int V> void run(const char *name, fe *d_in, fe *d_out, int blocks, int
 }
 
 int main() {
-    const int blocks = 148 * 8, iters = 2000, n = blocks * 256 + 8;
+    const int blocks = 148 * 8, iters = 2000, n = blocks * 256 + 16;
     std::vector<fe> h(n);
     unsigned long long s = 88172645463325252ULL;
     auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
@@ -88,6 +140,9 @@ int main() {
     run<2>("v3", d_in, d_out, blocks, iters);
 #endif
     run<3>("v4", d_in, d_out, blocks, iters);
+    run_call<0>("bfly inline", d_in, d_out, blocks, iters / 2);
+    run_call<1>("bfly 1 mul per call", d_in, d_out, blocks, iters / 2);
+    run_call<2>("bfly 2 muls per call", d_in, d_out, blocks, iters / 2);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }

@@ -11,15 +11,17 @@ src, prefix = sys.argv[1], sys.argv[2]
 rows = [r for r in csv.reader(l for l in open(src) if l.startswith('"'))]
 hdr, rows = rows[0], rows[1:]
 ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
-per_proof = int(sys.argv[3]) if len(sys.argv) > 3 else None
-if per_proof is None:
-    # the capture holds warm-up launches + identical proofs: the proof length is the distance between the last two constraint kernels
-    idx = [i for i, r in enumerate(rows) if "constraint_eval_kernel" in r[ki]]
-    per_proof = idx[-1] - idx[-2]
-last = rows[-per_proof:]
+# the capture holds warm-up launches, identical proofs and possibly other work after them: one steady-state proof's worth of launches
+# is the window between the last two constraint kernels (stages 4-9 of one proof + stages 1-3 of the next: same kernels, rotated)
+idx = [i for i, r in enumerate(rows) if "constraint_eval_kernel" in r[ki]]
+if len(sys.argv) > 3:
+    per_proof = int(sys.argv[3])
+    last = rows[-per_proof:]
+else:
+    last = rows[idx[-2] + 1: idx[-1] + 1]
 short = lambda k: re.sub(r"\(.*", "", k).replace("void ", "").replace("dg::", "")
 with open(prefix + "_launches_full.csv", "w") as f:
-    f.write(f"# launches of one proof (the last of the capture), in order; source: {src}\n# index,kernel,grid,block,ns\n")
+    f.write(f"# launches of one steady-state proof (window between the last two constraint kernels of the capture), in order; source: {src}\n# index,kernel,grid,block,ns\n")
     for i, r in enumerate(last):
         f.write(f"{i},{short(r[ki])},{r[gi].replace(',', ' ')},{r[bi].replace(',', ' ')},{r[vi]}\n")
 tot = OrderedDict()
@@ -31,7 +33,7 @@ for r in last:
 total = sum(t[1] for t in tot.values())
 with open(prefix + "_launches_summary.csv", "w") as f:
     f.write("# ncu launch list summary: one proof of the 2^20-step collatz trace (w=26, blowup 32) -- gpu__time_duration.sum, --clock-control none\n")
-    f.write("# command: ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/prove_once.py 20 3   (last proof)\n")
+    f.write("# command: " + (sys.argv[4] if len(sys.argv) > 4 else "ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline") + "\n")
     f.write("# per-launch times are cold-cache and serialised: compare SHARES with bench.py's stage_ms, not absolutes\n")
     f.write(f"# total {total:.2f} ms over {len(last)} launches\nkernel,launches,total_ms,share\n")
     for k, (n, ms) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
