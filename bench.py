@@ -257,6 +257,13 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg_bytes / n_pass, "launch_ms": lde / n_pass,
                 "note": "the kernel is integer-ALU bound, not HBM bound: ncu shows the ALU pipe 61-66% busy at 5% DRAM throughput "
                         "(profiles/r01_ncu_ntt_pass_kernel.txt); 2-pass NTT traffic = write + re-read of the 2^25-point intermediate"}
+    # the bound that actually applies: 128-bit modular arithmetic.  One LDE column = 32 coset NTTs of n points = 32 * (n/2) * log2(n)
+    # butterflies (1 modmul + 1 add + 1 sub) + 2 extra modmuls per point (coset factor, inter-pass twiddle), counted as 0.6 butterflies
+    bfly = cols * 32.0 * ((n / 2) * log_n + 0.6 * 2 * n)
+    peak_bfly = 224.6e9                         # tools/bench_modmul.cu, fe_mul v4 butterfly mix on B200 (profiles/r01_modmul_microbench.txt)
+    roofline["compute"] = {"bound": "integer ALU pipe (128-bit modular butterflies)", "unit": "G butterflies/s", "achieved": bfly / (lde * 1e-3) / 1e9,
+                           "peak": peak_bfly / 1e9, "frac": bfly / (lde * 1e-3) / peak_bfly,
+                           "peak_source": "profiles/r01_modmul_microbench.txt (arithmetic in isolation, same GPU model)"}
 
     # ---- CPU baseline: the oracle (restated reference prover) on a bounded sample, 1 thread
     cpu = {"value": None, "unit": "ms", "cores": 1, "kind": "port", "sample": "skipped (--no-cpu-baseline)"}
