@@ -167,3 +167,21 @@ def test_sharded_tree_index_algebra(L):
                 assert h < 2 * n * G and idx == h
             else:
                 assert local[owner][1][idx] == glob[h], (n, log_blk, log_g, h)
+
+
+def test_crafted_multiplication_operands_are_what_they_claim():
+    """tools/gen_mul_vectors.py (used by the GPU arithmetic tests): canonical operands whose product is a tiny / near-M residue"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gen_mul_vectors as g
+    pairs = g.pairs()
+    assert len(pairs) >= 400
+    small = 0
+    for a, b in pairs:
+        assert 0 <= a < g.M and 0 < b < g.M
+        r = a * b % g.M
+        if r < 2**94 or r > g.M - 2**97:
+            small += 1
+    assert small == len(pairs)
+    assert g.pairs() == pairs                                   # deterministic
