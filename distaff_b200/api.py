@@ -165,9 +165,9 @@ def find_pow_nonce(seed, grinding_factor=20):
 
 
 def field_op(op, a, b=None, impl=0):
-    code = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "exp": 4}[op]
+    code = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "exp": 4, "dot6": 5}[op]
     fa = np.ascontiguousarray(a, dtype=np.uint64)
     fb = np.ascontiguousarray(b, dtype=np.uint64) if b is not None else None
     out = np.empty_like(fa)
     backend.check(backend.lib().dg_field_op(code, impl, fa.ctypes.data, fb.ctypes.data if fb is not None else None, out.ctypes.data, fa.shape[0]))
-    return out
+    return out[:fa.shape[0] // 6] if op == "dot6" else out

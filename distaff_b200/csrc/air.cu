@@ -60,10 +60,7 @@ __device__ __forceinline__ void matvec(const fe *m, fe *s) {
     fe r[W];
 #pragma unroll
     for (int i = 0; i < W; i++) {
-        fe acc = fe_mul(m[i * W], s[0]);
-#pragma unroll
-        for (int j = 1; j < W; j++) acc = fe_add(acc, fe_mul(m[i * W + j], s[j]));
-        r[i] = acc;
+        r[i] = fe_dot<W>(m + i * W, s);          // one reduction per row: the W products are accumulated unreduced
         DG_STEP();
     }
 #pragma unroll
@@ -79,11 +76,13 @@ __device__ __forceinline__ fe is_bin(fe v) { return fe_sub(fe_sqr(v), v); }
 enum { G2 = 0, G3 = 1, G4 = 2, G6 = 3, G7 = 4, G8 = 5 };
 
 struct Acc {
-    fe res, adj[6];
+    fe_wide res;                        // sum_i v_i * cA_i, unreduced (at most 78 constraints < 128 products)
+    fe adj[6];
     const fe *cA, *cB;
-    bool nonzero;
+    bool nonzero, first;
     __device__ __forceinline__ void fold(int idx, int group, fe v) {
-        res = fe_add(res, fe_mul(v, cA[idx]));
+        if (first) { wide_set(res, DG_MUL_WIDE(v, cA[idx])); first = false; }
+        else wide_add(res, DG_MUL_WIDE(v, cA[idx]));
         adj[group] = fe_add(adj[group], fe_mul(v, cB[idx]));
         nonzero = nonzero || !fe_is_zero(v);
     }
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_kernel(cons
     }
 
     Acc acc;
-    acc.res = ZERO;
+    acc.first = true;
 #pragma unroll
     for (int g = 0; g < 6; g++) acc.adj[g] = ZERO;
     acc.cA = P.coefA; acc.cB = P.coefB; acc.nonzero = false;
@@ -483,7 +482,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_kernel(cons
 
     DG_STEP();
     // ---- combine (evaluator.rs:335-358): result + sum_g adj_g * x^inc_g ------------------------------------------------------------------
-    fe t_res = acc.res;
+    fe t_res = DG_REDUCE_WIDE(acc.res);
 #pragma unroll
     for (int g = 0; g < 6; g++) t_res = fe_add(t_res, fe_mul(acc.adj[g], tw_pow(P.twN, lde_index * P.inc[g])));
     // on the trace domain (except its last step) every constraint must vanish (evaluator.rs:149-158)

@@ -63,6 +63,15 @@ __global__ void coset_to_logical_kernel(const fe *__restrict__ in, fe *__restric
 __global__ void field_op_kernel(int op, int impl, const fe *a, const fe *b, fe *out, unsigned long long n) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (op == 5) {                    // unreduced dot product of groups of 6: out[i] = sum_j a[6i+j] * b[6i+j]; impl 0 = 288-bit accumulation, 1 = reduced
+        if (6 * i + 6 > n) return;
+        fe xs[6], ys[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) { xs[j] = a[6 * i + j]; ys[j] = b[6 * i + j]; }
+        if (impl == 0) out[i] = fe_dot<6>(xs, ys);
+        else { fe acc = portable::fe_mul(xs[0], ys[0]); for (int j = 1; j < 6; j++) acc = portable::fe_add(acc, portable::fe_mul(xs[j], ys[j])); out[i] = acc; }
+        return;
+    }
     fe x = a[i], y = b ? b[i] : fe_make(0, 0), r;
     if ((impl == 2 || impl == 3) && op == 2) {
 #ifdef __CUDA_ARCH__

@@ -85,6 +85,10 @@ __host__ __device__ inline fe fe_inv(fe a) { return fe_pow_u128(a, DG_M_LO - 2UL
 
 }  // namespace portable
 
+// unreduced accumulators (see the ptx namespace): 288-bit sums of products / one 256-bit product
+struct fe_wide { unsigned int r[9]; };
+struct fe_prod { unsigned int r[8]; };
+
 #ifdef __CUDA_ARCH__
 namespace ptx {
 
@@ -443,6 +447,71 @@ __device__ __forceinline__ fe fe_mul_v4t(fe a, fe b) {
     return fe_reduce_v4<NESTED_CALL>(r);
 }
 __device__ __forceinline__ fe fe_mul_v4(fe a, fe b) { return fe_mul_v4t<true>(a, b); }
+// ---- unreduced accumulation: sums of up to 128 products are kept as 288-bit integers and reduced once ------------------------------
+// A dot product sum_j a_j b_j costs, per term, one 256-bit product (16 IMAD.WIDE + 13 ALU) and one 9-limb addition (9 ALU) instead of a
+// full modular multiplication and a modular addition (31 + 13 ALU); the single reduction at the end is the v4 fold extended by one limb
+// (tools/model_reduce9.py checks every intermediate bound of it against Python integers).
+__device__ __forceinline__ fe_prod fe_mul_wide(fe a, fe b) {
+    unsigned int x[4] = { (unsigned int)a.lo, (unsigned int)(a.lo >> 32), (unsigned int)a.hi, (unsigned int)(a.hi >> 32) };
+    unsigned int y[4] = { (unsigned int)b.lo, (unsigned int)(b.lo >> 32), (unsigned int)b.hi, (unsigned int)(b.hi >> 32) };
+    fe_prod p;
+    mul_wide_eo(x, y, p.r);
+    return p;
+}
+__device__ __forceinline__ void wide_set(fe_wide &w, const fe_prod &p) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) w.r[i] = p.r[i];
+    w.r[8] = 0;
+}
+__device__ __forceinline__ void wide_add(fe_wide &w, const fe_prod &p) {
+    asm("add.cc.u32  %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\t"
+        "addc.cc.u32 %6, %6, %15;\n\t"
+        "addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32    %8, %8, 0;"
+        : "+r"(w.r[0]), "+r"(w.r[1]), "+r"(w.r[2]), "+r"(w.r[3]), "+r"(w.r[4]), "+r"(w.r[5]), "+r"(w.r[6]), "+r"(w.r[7]), "+r"(w.r[8])
+        : "r"(p.r[0]), "r"(p.r[1]), "r"(p.r[2]), "r"(p.r[3]), "r"(p.r[4]), "r"(p.r[5]), "r"(p.r[6]), "r"(p.r[7]));
+}
+// w (< 128 M^2, i.e. r[8] < 128) modulo M, canonical
+__device__ __forceinline__ fe fe_reduce_wide(const fe_wide &w) {
+    const unsigned int K = 11520u;
+    const unsigned int *r = w.r;
+    // V = lo + ((H * K) << 32) - H,  H = r[4..8]
+    unsigned long long t0 = wmad(r[4], K, (unsigned long long)r[1]);
+    unsigned long long t1 = wmad(r[2], 1u, wmad(r[5], K, t0 >> 32));
+    unsigned long long t2 = wmad(r[3], 1u, wmad(r[6], K, t1 >> 32));
+    unsigned long long t3 = wmad(r[7], K, t2 >> 32);
+    unsigned long long t4 = wmad(r[8], K, t3 >> 32);
+    unsigned int v0 = r[0], v1 = (unsigned int)t0, v2 = (unsigned int)t1, v3 = (unsigned int)t2, v4 = (unsigned int)t3, v5 = (unsigned int)t4;
+    asm("sub.cc.u32  %0, %0, %6;\n\t"
+        "subc.cc.u32 %1, %1, %7;\n\t"
+        "subc.cc.u32 %2, %2, %8;\n\t"
+        "subc.cc.u32 %3, %3, %9;\n\t"
+        "subc.cc.u32 %4, %4, %10;\n\t"
+        "subc.u32    %5, %5, 0;"
+        : "+r"(v0), "+r"(v1), "+r"(v2), "+r"(v3), "+r"(v4), "+r"(v5) : "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]));
+    // the limb above v5 is zero (V < 2^181); fold T = v5:v4 (< 2^53)
+    unsigned long long u1 = wmad(v4, K, (unsigned long long)v1);
+    unsigned long long u2 = wmad(v2, 1u, wmad(v5, K, u1 >> 32));
+    unsigned long long u3 = wmad(v3, 1u, u2 >> 32);
+    v1 = (unsigned int)u1; v2 = (unsigned int)u2; v3 = (unsigned int)u3;
+    unsigned int cy = (unsigned int)(u3 >> 32);
+    asm("sub.cc.u32  %0, %0, %5;\n\t"
+        "subc.cc.u32 %1, %1, %6;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.u32    %4, %4, 0;"
+        : "+r"(v0), "+r"(v1), "+r"(v2), "+r"(v3), "+r"(cy) : "r"(v4), "r"(v5));
+    if (__builtin_expect((cy != 0u) | (v3 == 0xffffffffu), 0)) return fe_canon_inline(v0, v1, v2, v3, cy);
+    fe out;
+    out.lo = ((unsigned long long)v1 << 32) | v0;
+    out.hi = ((unsigned long long)v3 << 32) | v2;
+    return out;
+}
 // the multiply used by every kernel (tools/bench_modmul.cu on B200: v1 228, v3 274, v4 292 G modmul/s; butterfly mix 183 / 199 / 224 G/s)
 #ifdef DG_MUL_CALL
 // out-of-line variant for kernels whose fully inlined code would not fit the instruction caches
@@ -515,6 +584,45 @@ __host__ __device__ __forceinline__ fe fe_mul_small(fe a, unsigned int k) {
 #endif
 }
 #undef DG_IMPL
+
+// ---- unreduced dot products: device = 288-bit accumulation (ptx::), host = the same values through reduced arithmetic ----------------
+#ifdef __CUDA_ARCH__
+#ifdef DG_MUL_CALL
+static __device__ __noinline__ fe_prod fe_mul_wide_call(fe a, fe b) { return ptx::fe_mul_wide(a, b); }
+static __device__ __noinline__ fe fe_reduce_wide_call(fe_wide w) { return ptx::fe_reduce_wide(w); }
+#define DG_MUL_WIDE fe_mul_wide_call
+#define DG_REDUCE_WIDE fe_reduce_wide_call
+#else
+#define DG_MUL_WIDE ptx::fe_mul_wide
+#define DG_REDUCE_WIDE ptx::fe_reduce_wide
+#endif
+__device__ __forceinline__ void wide_set(fe_wide &w, const fe_prod &p) { ptx::wide_set(w, p); }
+__device__ __forceinline__ void wide_add(fe_wide &w, const fe_prod &p) { ptx::wide_add(w, p); }
+#else
+// host pass: a product is carried already reduced in its low four limbs
+inline fe_prod fe_mul_wide_host(fe a, fe b) {
+    fe m = portable::fe_mul(a, b);
+    fe_prod p = {{(unsigned int)m.lo, (unsigned int)(m.lo >> 32), (unsigned int)m.hi, (unsigned int)(m.hi >> 32), 0, 0, 0, 0}};
+    return p;
+}
+inline fe fe_reduce_wide_host(fe_wide w) { return fe_make(((unsigned long long)w.r[1] << 32) | w.r[0], ((unsigned long long)w.r[3] << 32) | w.r[2]); }
+#define DG_MUL_WIDE fe_mul_wide_host
+#define DG_REDUCE_WIDE fe_reduce_wide_host
+inline void wide_set(fe_wide &w, const fe_prod &p) { for (int i = 0; i < 8; i++) w.r[i] = p.r[i]; w.r[8] = 0; }
+inline void wide_add(fe_wide &w, const fe_prod &p) {
+    fe s = portable::fe_add(fe_reduce_wide_host(w), fe_make(((unsigned long long)p.r[1] << 32) | p.r[0], ((unsigned long long)p.r[3] << 32) | p.r[2]));
+    w.r[0] = (unsigned int)s.lo; w.r[1] = (unsigned int)(s.lo >> 32); w.r[2] = (unsigned int)s.hi; w.r[3] = (unsigned int)(s.hi >> 32);
+}
+#endif
+// sum_j a[j] * b[j], N <= 128 terms (compile-time N: fully unrolled)
+template <int N>
+__host__ __device__ __forceinline__ fe fe_dot(const fe *a, const fe *b) {
+    fe_wide w;
+    wide_set(w, DG_MUL_WIDE(a[0], b[0]));
+#pragma unroll
+    for (int j = 1; j < N; j++) wide_add(w, DG_MUL_WIDE(a[j], b[j]));
+    return DG_REDUCE_WIDE(w);
+}
 
 
 }  // namespace dg

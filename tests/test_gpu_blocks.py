@@ -68,6 +68,23 @@ def test_mul_crafted_reduction_paths(dg):
         assert felt.to_ints(dg.field_op("sub", fa, fb, impl=impl)) == [(x - y) % M for x, y in zip(xs, ys)], impl
 
 
+def test_unreduced_dot_products(dg):
+    """288-bit accumulation of 6 products reduced once (fe_dot, used by the constraint kernel's mat-vecs) == Python integers;
+    operands include the crafted pairs and all-(M-1) rows (largest accumulator)"""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gen_mul_vectors
+    from distaff_b200 import felt
+    pairs = gen_mul_vectors.pairs()
+    xs = [p[0] for p in pairs] + [M - 1] * 60 + felt.to_ints(_rand(6000, 31))
+    ys = [p[1] for p in pairs] + [M - 1] * 60 + felt.to_ints(_rand(6000, 32))
+    n = len(xs) // 6 * 6
+    xs, ys = xs[:n], ys[:n]
+    want = [sum(xs[6 * i + j] * ys[6 * i + j] for j in range(6)) % M for i in range(n // 6)]
+    for impl in (0, 1):
+        assert felt.to_ints(dg.field_op("dot6", felt.from_ints(xs), felt.from_ints(ys), impl=impl)) == want, impl
+
+
 @pytest.mark.parametrize("log_n", [1, 2, 3, 4, 5, 8, 10, 11, 12, 13, 16, 19, 20, 21, 22])
 def test_ntt_matches_oracle(dg, po, log_n):
     n = 1 << log_n
