@@ -48,3 +48,13 @@ def small_programs():
         "begin push.2 push.1 while.true push.3 push.1 while.true push.1 neg add dup push.0 ne end drop push.1 neg add dup push.0 ne end end",
         num_outputs=1)
     return P
+
+
+def wide_program():
+    """65 registers (ctx 15, loop 3, stack 32): every extended-trace row is 1040 bytes = two BLAKE3 chunks + a parent node
+    (trace_table.rs:174-185 with w > 64).  Kept out of small_programs(): the golden file and the GPU parametrisations are per name."""
+    from distaff_b200 import hostvm
+    loop = ("push.2 push.1 while.true push.2 push.1 while.true push.2 push.1 while.true push.1 neg add dup push.0 ne end drop "
+            "push.1 neg add dup push.0 ne end drop push.1 neg add dup push.0 ne end drop")
+    src = "begin " + " ".join(f"push.{i + 1}" for i in range(26)) + " " + "block push.1 add " * 15 + "end " * 15 + " " + loop + " end"
+    return hostvm.execute(src, num_outputs=2)

@@ -72,3 +72,15 @@ def test_matches_golden_digests(proven):
         assert r.digest("constraint_root").hex() == g["constraint_root"]
         assert r.u64s("pow_nonce")[0] == g["pow_nonce"]
         assert r.u64s("positions")[:5] == g["positions5"]
+
+
+def test_wide_trace_two_chunk_rows(po):
+    """w = 65 > 64 registers: leaves are multi-chunk BLAKE3 hashes; the restated prover and verifier still agree"""
+    tr = programs.wide_program()
+    assert (tr.width, tr.ctx_depth, tr.loop_depth, tr.stack_depth) == (65, 15, 3, 32)
+    r = po.prove(tr.registers, tr.ctx_depth, tr.loop_depth, tr.public_inputs, tr.outputs, num_queries=20, grinding=8)
+    assert r.error is None
+    assert po.verify(tr.program_hash, tr.public_inputs, tr.outputs, r.proof) is None
+    bad = bytearray(r.proof)
+    bad[40] ^= 1
+    assert po.verify(tr.program_hash, tr.public_inputs, tr.outputs, bytes(bad)) is not None
