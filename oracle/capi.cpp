@@ -254,6 +254,13 @@ uint32_t or_eval_transition_raw(const uint8_t *cur_row, const uint8_t *next_row,
     memcpy(out, ev.data(), ev.size() * 16);
     return (uint32_t)ev.size();
 }
+// utils::sponge::apply_round (sponge.rs:13-30) on a 4-element state, in place
+void or_sponge_round(uint8_t *state4, const uint8_t *op_code, const uint8_t *op_value, uint64_t step) {
+    u128 s[4], c, v;
+    memcpy(s, state4, 64); memcpy(&c, op_code, 16); memcpy(&v, op_value, 16);
+    sponge4::apply_round(s, c, v, step);
+    memcpy(state4, s, 64);
+}
 // op flags of a row: out = cf[8] ld[32] hd[4] begin noop  (46 elements)
 void or_op_flags(const uint8_t *row, uint32_t cd, uint32_t ldp, uint32_t sd, uint8_t *out) {
     TraceState c(cd, ldp, sd);

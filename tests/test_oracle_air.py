@@ -64,3 +64,92 @@ def test_transition_constraints_vanish_on_vm_traces(po):
         k = po.lib().or_eval_transition_raw(cur.ctypes.data, nxt.ctypes.data, tr.ctx_depth, tr.loop_depth, tr.stack_depth,
                                             n, 3 * 8, out.ctypes.data)
         assert any(v != 0 for v in po.ints(out[:k]))
+
+
+def test_decoder_flow_ops_reference_vectors(po):
+    """the literal expected vectors of the reference's own unit tests for enforce_{begin,tend,fend,loop,wrap,break,void}
+    (/root/reference/src/stark/constraints/decoder/flow_ops.rs mod tests; fixture: tests/golden/ref_decoder_flow_cases.json, made by
+    tests/golden/make_ref_decoder_cases.py).  The reference calls one enforce_* with op_flag = 1; here the first state carries the op
+    bits of that operation, so the oracle's full decoder evaluation has exactly that flag set."""
+    import json
+    import os
+    from distaff_b200 import felt
+    flow_code = {"hacc": 0, "begin": 1, "tend": 2, "fend": 3, "loop": 4, "wrap": 5, "break": 6, "void": 7}
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_decoder_flow_cases.json")))["cases"]
+    assert len(cases) == 30
+
+    def row(st, code):
+        v = [st["step"]] + st["sponge"] + [(code >> i) & 1 for i in range(3)] + [1] * 7 + st["ctx"] + st["loop"] + [101]
+        return felt.from_ints(v)
+
+    out = np.zeros((64, 2), dtype=np.uint64)
+    for c in cases:
+        cd, ld = len(c["state1"]["ctx"]), len(c["state1"]["loop"])
+        assert c["op_flag"] == 1 and len(c["state2"]["ctx"]) == cd and len(c["state2"]["loop"]) == ld
+        cur = row(c["state1"], flow_code[c["op"]])
+        nxt = row(c["state2"], flow_code[c["state2"]["flow_op"].lower()])
+        k = po.lib().or_eval_transition_raw(cur.ctypes.data, nxt.ctypes.data, cd, ld, 1, 16, 8 * c["state1"]["step"], out.ctypes.data)
+        want = [int(x) for x in c["expected"]]
+        got = po.ints(out[:k])[15:15 + len(want)]
+        assert got == want, (c["op"], c["state1"], c["state2"], got)
+
+
+def _sponge_round(po, state, op_code, op_value, step):
+    from distaff_b200 import felt
+    st = felt.from_ints(state)
+    c, v = felt.from_ints([op_code]), felt.from_ints([op_value])
+    po.lib().or_sponge_round(st.ctypes.data, c.ctypes.data, v.ctypes.data, step)
+    return felt.to_ints(st)
+
+
+def _decoder_eval(po, cur, nxt, cd, ld, step):
+    from distaff_b200 import felt
+    out = np.zeros((64, 2), dtype=np.uint64)
+    a, b = felt.from_ints(cur), felt.from_ints(nxt)
+    k = po.lib().or_eval_transition_raw(a.ctypes.data, b.ctypes.data, cd, ld, 1, 16, step, out.ctypes.data)
+    return po.ints(out[:k])[:20 + max(cd, 1) + max(ld, 1)]          # decoder constraints only
+
+
+def test_decoder_hacc_reference_vectors(po):
+    """decoder/sponge.rs mod tests (op_hacc): literal expectations 0 / M - 1 / M - 9 for the four sponge constraints"""
+    M = 2**128 - 45 * 2**40 + 1
+    push = [0, 1, 2, 3, 4, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0]            # HACC + PUSH  (op code = 0b00_11111 = 31)
+    other = [0, 1, 2, 3, 4, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 0, 0]           # HACC + an op with hd = 11, ld = 00000 (op code 96)
+
+    def build_state(sponge, push_value):
+        return [0] + list(sponge) + [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, push_value]
+
+    def op_code(state):
+        return sum(state[8 + i] << i for i in range(5)) + (state[13] << 5) + (state[14] << 6)
+
+    cases = [(push, 7, 7, [0, 0, 0, 0]), (other, 0, 9, [0, 0, 0, 0]), (push, 7, 6, [0, M - 1, 0, 0]), (other, 9, 9, [0, M - 9, 0, 0])]
+    for state1, absorbed, next_top, want in cases:
+        sponge = _sponge_round(po, [1, 2, 3, 4], op_code(state1), absorbed, 0)
+        got = _decoder_eval(po, state1, build_state(sponge, next_top), 1, 0, 0)[15:19]
+        assert got == want, (state1, got)
+
+
+def test_decoder_begin_and_hacc_transitions(po):
+    """decoder/tests.rs: enforce_begin / enforce_hacc through the whole Decoder::evaluate (trace length 16, extension 8)"""
+    ok = lambda ev: all(v == 0 for v in ev)
+    step = 15 * 8
+    s1 = [0, 3, 5, 7, 9, 1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 11]
+    assert ok(_decoder_eval(po, s1, [0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3, 11], 1, 0, step))
+    assert not ok(_decoder_eval(po, [0, 3, 5, 7, 9, 1, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0, 11], [0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3, 11], 1, 0, step))
+    assert not ok(_decoder_eval(po, s1, [0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 11], 1, 0, step))
+    assert not ok(_decoder_eval(po, s1, [0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 5, 11], 1, 0, step))
+    assert not ok(_decoder_eval(po, s1, [0, 3, 5, 7, 9, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 3, 11], 1, 0, step))
+
+    PUSH, ADD = 0b0011111, 0b1101000                     # processor/opcodes.rs:46-92 (hd bits | ld bits)
+    def hacc(state1, state2, code, value, sponge_step, eval_step):
+        st2 = list(state2)
+        st2[1:5] = _sponge_round(po, st2[1:5], code, value, sponge_step)
+        return _decoder_eval(po, state1, st2, 1, 0, eval_step)
+    p1 = [1, 3, 5, 7, 9, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 11]
+    assert ok(hacc(p1, [2, 3, 5, 7, 9, 1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 9], PUSH, 9, 0, 0))
+    assert ok(hacc(p1, [2, 3, 5, 7, 9, 1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 9], PUSH, 9, 8, 8 * 8))
+    a1 = [1, 3, 5, 7, 9, 0, 0, 0, 0, 0, 0, 1, 0, 1, 1, 0, 0]
+    assert ok(hacc(a1, [2, 3, 5, 7, 9, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 0], ADD, 0, 0, 0))
+    assert not ok(hacc(p1, [2, 3, 5, 7, 9, 1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 11], PUSH, 9, 0, 0))
+    assert not ok(hacc([1, 3, 5, 7, 9, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 11], [2, 3, 5, 7, 9, 1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 9], PUSH, 9, 0, 0))
+    assert not ok(hacc([1, 3, 5, 7, 9, 0, 0, 0, 0, 0, 0, 1, 0, 1, 1, 0, 9], [2, 3, 5, 7, 9, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 0], ADD, 9, 0, 0))
