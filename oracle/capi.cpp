@@ -254,6 +254,22 @@ uint32_t or_eval_transition_raw(const uint8_t *cur_row, const uint8_t *next_row,
     memcpy(out, ev.data(), ev.size() * 16);
     return (uint32_t)ev.size();
 }
+// Decoder::evaluate with explicit periodic values (ark[8], masks[3]) instead of a step: what the reference's unit tests of
+// enforce_op_bits / enforce_hacc pass in (decoder/op_bits.rs, decoder/sponge.rs mod tests)
+uint32_t or_decoder_run_raw(const uint8_t *cur_row, const uint8_t *next_row, uint32_t cd, uint32_t ldp, uint32_t sd,
+                            const uint8_t *ark8, const uint8_t *masks3, uint8_t *out) {
+    TraceState c(cd, ldp, sd), n(cd, ldp, sd);
+    std::vector<u128> rc(c.width()), rn(c.width());
+    memcpy(rc.data(), cur_row, rc.size() * 16); memcpy(rn.data(), next_row, rn.size() * 16);
+    c.from_row(rc.data()); n.from_row(rn.data());
+    DecoderAir dec(16, 8, cd, ldp);
+    u128 ark[8], masks[3];
+    memcpy(ark, ark8, sizeof ark); memcpy(masks, masks3, sizeof masks);
+    std::vector<u128> ev(dec.constraint_count(), 0);
+    dec.run(c, n, ark, masks, ev.data());
+    memcpy(out, ev.data(), ev.size() * 16);
+    return (uint32_t)ev.size();
+}
 // utils::sponge::apply_round (sponge.rs:13-30) on a 4-element state, in place
 void or_sponge_round(uint8_t *state4, const uint8_t *op_code, const uint8_t *op_value, uint64_t step) {
     u128 s[4], c, v;

@@ -153,3 +153,57 @@ def test_decoder_begin_and_hacc_transitions(po):
     assert not ok(hacc(p1, [2, 3, 5, 7, 9, 1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 11], PUSH, 9, 0, 0))
     assert not ok(hacc([1, 3, 5, 7, 9, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 11], [2, 3, 5, 7, 9, 1, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 9], PUSH, 9, 0, 0))
     assert not ok(hacc([1, 3, 5, 7, 9, 0, 0, 0, 0, 0, 0, 1, 0, 1, 1, 0, 9], [2, 3, 5, 7, 9, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 0, 0], ADD, 9, 0, 0))
+
+
+def test_decoder_op_bits_reference_tests(po):
+    """decoder/op_bits.rs mod tests: op_bits_are_binary (literal 3*3 - 3 at the offending position), invalid_op_combinations,
+    invalid_op_alignment and invalid_op_sequence, with the masks passed explicitly as the reference tests do"""
+    from distaff_b200 import felt
+    NOOP, PUSH, ADD = 0b1111111, 0b0011111, 0b1101000
+    HACC, BEGIN, TEND, FEND, LOOP, WRAP, BREAK, VOID = range(8)
+
+    def state(flow, user, counter=0, cf_bits=None, u_bits=None):
+        cf = cf_bits if cf_bits is not None else [(flow >> i) & 1 for i in range(3)]
+        ub = u_bits if u_bits is not None else [(user >> i) & 1 for i in range(7)]
+        return [counter, 0, 0, 0, 0] + cf + ub + [0, 0]                 # ctx depth 1, loop depth 0, stack depth 1
+
+    def op_bits(cur, nxt, masks):
+        out = np.zeros((64, 2), dtype=np.uint64)
+        a, b = felt.from_ints(cur), felt.from_ints(nxt)
+        ark, mk = felt.from_ints([0] * 8), felt.from_ints(masks)
+        po.lib().or_decoder_run_raw(a.ctypes.data, b.ctypes.data, 1, 0, 1, ark.ctypes.data, mk.ctypes.data, out.ctypes.data)
+        return po.ints(out[:15])
+
+    def evaluate_state(st, masks, inc_counter):
+        return op_bits(st, state(VOID, NOOP, st[0] + (1 if inc_counter else 0)), masks)
+
+    ok = [0] * 15
+    # op_bits_are_binary
+    assert evaluate_state(state(VOID, NOOP, 1), [0, 0, 0], False) == ok
+    for i in range(3):
+        cf = [1, 1, 1]; cf[i] = 3
+        want = [0] * 10; want[i] = 3 * 3 - 3
+        assert evaluate_state(state(0, 0, 0, cf_bits=cf, u_bits=[1] * 7), [0, 0, 0], False)[:10] == want
+    for i in range(7):
+        ub = [1] * 7; ub[i] = 3
+        want = [0] * 10; want[i + 3] = 3 * 3 - 3
+        assert evaluate_state(state(0, 0, 0, cf_bits=[0, 0, 0], u_bits=ub), [0, 0, 0], False)[:10] == want
+    # invalid_op_combinations
+    for cf_op in range(8):
+        assert evaluate_state(state(cf_op, 0, 1), [0, 0, 0], False) != ok
+    for cf_op in range(1, 8):
+        for user_op in range(127):
+            assert evaluate_state(state(cf_op, user_op, 1), [0, 0, 0], False) != ok
+        assert evaluate_state(state(cf_op, NOOP, 1), [0, 0, 0], False) == ok
+    # invalid_op_alignment
+    for flow, bad in ((TEND, [1, 0, 0]), (FEND, [1, 0, 0]), (BEGIN, [0, 1, 0]), (LOOP, [0, 1, 0]), (WRAP, [0, 1, 0]), (BREAK, [0, 1, 0])):
+        st = state(flow, NOOP, 1)
+        assert evaluate_state(st, [0, 0, 0], False) == ok
+        assert evaluate_state(st, bad, False) != ok
+    st = state(HACC, PUSH, 1)
+    assert evaluate_state(st, [0, 0, 0], True) == ok
+    assert evaluate_state(st, [0, 0, 1], True) != ok
+    # invalid_op_sequence
+    assert op_bits(state(HACC, ADD, 1), state(VOID, NOOP, 2), [0, 0, 0]) == ok
+    assert op_bits(state(VOID, NOOP, 1), state(VOID, NOOP, 1), [0, 0, 0]) == ok
+    assert op_bits(state(VOID, NOOP, 1), state(HACC, ADD, 1), [0, 0, 0]) != ok
