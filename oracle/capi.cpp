@@ -270,6 +270,14 @@ uint32_t or_decoder_run_raw(const uint8_t *cur_row, const uint8_t *next_row, uin
     memcpy(out, ev.data(), ev.size() * 16);
     return (uint32_t)ev.size();
 }
+// constraints::utils::enforce_left_shift (utils.rs:64-83) on plain vectors of length len
+void or_enforce_left_shift(const uint8_t *old_stack, const uint8_t *new_stack, uint64_t len, uint64_t from, uint64_t num, const uint8_t *flag, uint8_t *result) {
+    std::vector<u128> o(len), n(len), r(len, 0);
+    u128 f;
+    memcpy(o.data(), old_stack, len * 16); memcpy(n.data(), new_stack, len * 16); memcpy(&f, flag, 16);
+    cu::left_shift(r.data(), len, o.data(), n.data(), from, num, f);
+    memcpy(result, r.data(), len * 16);
+}
 // utils::sponge::apply_round (sponge.rs:13-30) on a 4-element state, in place
 void or_sponge_round(uint8_t *state4, const uint8_t *op_code, const uint8_t *op_value, uint64_t step) {
     u128 s[4], c, v;

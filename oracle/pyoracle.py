@@ -69,6 +69,8 @@ def lib():
         L.or_op_flags.argtypes = [u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, u8p]
         L.or_decoder_run_raw.restype = ctypes.c_uint32
         L.or_decoder_run_raw.argtypes = [u8p, u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, u8p, u8p, u8p]
+        L.or_enforce_left_shift.restype = None
+        L.or_enforce_left_shift.argtypes = [u8p, u8p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, u8p, u8p]
         L.or_sponge_round.restype = None
         L.or_sponge_round.argtypes = [u8p, u8p, u8p, ctypes.c_uint64]
         _LIB = L

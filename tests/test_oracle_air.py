@@ -207,3 +207,14 @@ def test_decoder_op_bits_reference_tests(po):
     assert op_bits(state(HACC, ADD, 1), state(VOID, NOOP, 2), [0, 0, 0]) == ok
     assert op_bits(state(VOID, NOOP, 1), state(VOID, NOOP, 1), [0, 0, 0]) == ok
     assert op_bits(state(VOID, NOOP, 1), state(HACC, ADD, 1), [0, 0, 0]) != ok
+
+
+def test_enforce_left_shift_reference_vectors(po):
+    """constraints/utils.rs mod tests: the four literal vectors of enforce_left_shift"""
+    from distaff_b200 import felt
+    v = felt.from_ints([1, 2, 3, 4, 5, 6, 7, 8])
+    one = felt.from_ints([1])
+    for frm, num, want in ((1, 1, [1, 1, 1, 1, 1, 1, 1, 8]), (2, 2, [2, 2, 2, 2, 2, 2, 7, 8]), (2, 1, [0, 1, 1, 1, 1, 1, 1, 8]), (6, 4, [0, 0, 4, 4, 5, 6, 7, 8])):
+        out = np.zeros((8, 2), dtype=np.uint64)
+        po.lib().or_enforce_left_shift(v.ctypes.data, v.ctypes.data, 8, frm, num, one.ctypes.data, out.ctypes.data)
+        assert po.ints(out) == want, (frm, num)
