@@ -278,6 +278,23 @@ void or_enforce_left_shift(const uint8_t *old_stack, const uint8_t *new_stack, u
     cu::left_shift(r.data(), len, o.data(), n.data(), from, num, f);
     memcpy(result, r.data(), len * 16);
 }
+// TraceState::from_vec decoded (trace_state.rs:88-118): out = op_counter, sponge[4], cf[3], ld[5], hd[2], ctx[ctx_len], loop[loop_len],
+// user[stack_len], op_code; returns the number of elements written
+uint32_t or_trace_state_fields(const uint8_t *row, uint32_t cd, uint32_t ldp, uint32_t sd, uint8_t *out) {
+    TraceState c(cd, ldp, sd);
+    std::vector<u128> r(c.width());
+    memcpy(r.data(), row, r.size() * 16);
+    c.from_row(r.data());
+    std::vector<u128> v;
+    v.push_back(c.op_counter);
+    v.insert(v.end(), c.sponge, c.sponge + 4); v.insert(v.end(), c.cf_bits, c.cf_bits + 3);
+    v.insert(v.end(), c.ld_bits, c.ld_bits + 5); v.insert(v.end(), c.hd_bits, c.hd_bits + 2);
+    v.insert(v.end(), c.ctx_stack, c.ctx_stack + c.ctx_len); v.insert(v.end(), c.loop_stack, c.loop_stack + c.loop_len);
+    v.insert(v.end(), c.user_stack, c.user_stack + c.stack_len);
+    v.push_back(c.op_code());
+    memcpy(out, v.data(), v.size() * 16);
+    return (uint32_t)v.size();
+}
 // utils::sponge::apply_round (sponge.rs:13-30) on a 4-element state, in place
 void or_sponge_round(uint8_t *state4, const uint8_t *op_code, const uint8_t *op_value, uint64_t step) {
     u128 s[4], c, v;

@@ -218,3 +218,23 @@ def test_enforce_left_shift_reference_vectors(po):
         out = np.zeros((8, 2), dtype=np.uint64)
         po.lib().or_enforce_left_shift(v.ctypes.data, v.ctypes.data, 8, frm, num, one.ctypes.data, out.ctypes.data)
         assert po.ints(out) == want, (frm, num)
+
+
+def test_trace_state_layout_reference_vectors(po):
+    """trace_state.rs mod tests from_vec / op_code: register order (op_counter, sponge, cf, ld, hd, ctx, loop, user stack), zero padding
+    of the three stacks to at least 1 / 1 / 8 entries, and op_code = sum of the seven user-op bits weighted by powers of two"""
+    from distaff_b200 import felt
+
+    def fields(cd, ld, sd, row):
+        out = np.zeros((80, 2), dtype=np.uint64)
+        a = felt.from_ints(row)
+        k = po.lib().or_trace_state_fields(a.ctypes.data, cd, ld, sd, out.ctypes.data)
+        return po.ints(out[:k])
+
+    head = [101, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14]
+    assert fields(0, 0, 2, head + [15, 16])[:-1] == head + [0] + [0] + [15, 16, 0, 0, 0, 0, 0, 0]
+    assert fields(1, 0, 2, head + [15, 16, 17])[:-1] == head + [15] + [0] + [16, 17, 0, 0, 0, 0, 0, 0]
+    assert fields(2, 1, 9, head + list(range(15, 27)))[:-1] == head + [15, 16] + [17] + list(range(18, 27))
+    base = [101, 1, 2, 3, 4, 1, 1, 1]
+    for bits, code in (([0] * 7, 0), ([1] * 7, 127), ([1, 1, 1, 1, 1, 1, 0], 63), ([1, 0, 0, 0, 0, 1, 1], 97)):
+        assert fields(1, 0, 2, base + bits + [15, 16, 17])[-1] == code
