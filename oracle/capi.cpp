@@ -295,6 +295,27 @@ uint32_t or_trace_state_fields(const uint8_t *row, uint32_t cd, uint32_t ldp, ui
     memcpy(out, v.data(), v.size() * 16);
     return (uint32_t)v.size();
 }
+// stand-alone FRI round trip as in fri/mod.rs mod tests: reduce + build_proof over `evaluations` (domain = powers of the root of unity of
+// that size, default ProofOptions), then verify against max_degree with the first `drop` sampled evaluations removed.
+// Returns 0 and writes "" on success, else writes the verifier's error message (NUL terminated) into msg.
+int or_fri_roundtrip(const uint8_t *evaluations, uint64_t domain_size, uint64_t max_degree, uint32_t drop, char *msg, uint64_t cap) {
+    try {
+        std::vector<u128> ev(domain_size);
+        memcpy(ev.data(), evaluations, domain_size * 16);
+        std::vector<u128> domain = field::get_power_series(field::get_root_of_unity(domain_size), domain_size);
+        ProofOptions opt;
+        std::vector<MerkleTree> trees; std::vector<std::vector<quartic::Q>> values;
+        fri_reduce(ev, domain, hash_by_id(0), trees, values);
+        std::vector<size_t> positions = compute_query_positions(trees.back().root().data(), domain_size, opt.extension_factor, opt.num_queries);
+        FriProof proof = fri_build_proof(trees, values, positions);
+        std::vector<u128> sampled;
+        for (size_t p : positions) sampled.push_back(ev[p]);
+        sampled.erase(sampled.begin(), sampled.begin() + std::min<size_t>(drop, sampled.size()));
+        std::string err = fri_verify(proof, sampled, positions, max_degree, opt);
+        snprintf(msg, cap, "%s", err.c_str());
+        return err.empty() ? 0 : 1;
+    } catch (const std::exception &e) { snprintf(msg, cap, "exception: %s", e.what()); return -1; }
+}
 // utils::sponge::apply_round (sponge.rs:13-30) on a 4-element state, in place
 void or_sponge_round(uint8_t *state4, const uint8_t *op_code, const uint8_t *op_value, uint64_t step) {
     u128 s[4], c, v;

@@ -73,6 +73,8 @@ def lib():
         L.or_enforce_left_shift.argtypes = [u8p, u8p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, u8p, u8p]
         L.or_trace_state_fields.restype = ctypes.c_uint32
         L.or_trace_state_fields.argtypes = [u8p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, u8p]
+        L.or_fri_roundtrip.restype = ctypes.c_int
+        L.or_fri_roundtrip.argtypes = [u8p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64]
         L.or_sponge_round.restype = None
         L.or_sponge_round.argtypes = [u8p, u8p, u8p, ctypes.c_uint64]
         _LIB = L

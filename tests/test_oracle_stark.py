@@ -84,3 +84,27 @@ def test_wide_trace_two_chunk_rows(po):
     bad = bytearray(r.proof)
     bad[40] ^= 1
     assert po.verify(tr.program_hash, tr.public_inputs, tr.outputs, bytes(bad)) is not None
+
+
+def test_fri_round_trip_reference_tests(po):
+    """fri/mod.rs mod tests prove_verify / verify_fail: a random polynomial of degree 63 (64) over a 512-point domain, default options,
+    with the reference's exact error strings"""
+    import ctypes
+    import numpy as np
+    from distaff_b200 import felt
+
+    def evaluations(domain_size, degree, seed):
+        coeffs = felt.to_ints(felt.random_elements(degree + 1, seed)) + [0] * (domain_size - degree - 1)
+        return po.fft(felt.from_ints(coeffs))
+
+    def run(ev, max_degree, drop=0):
+        msg = ctypes.create_string_buffer(256)
+        rc = po.lib().or_fri_roundtrip(np.ascontiguousarray(ev).ctypes.data, ev.shape[0], max_degree, drop, msg, 256)
+        return rc, msg.value.decode()
+
+    ev = evaluations(512, 63, 11)
+    assert run(ev, 63) == (0, "")
+    assert run(ev, 62) == (1, "remainder is not a valid degree 14 polynomial")
+    ev2 = evaluations(512, 64, 12)
+    assert run(ev2, 63) == (1, "remainder is not a valid degree 15 polynomial")
+    assert run(ev2, 63, drop=1) == (1, "evaluations did not match column value at depth 0")
