@@ -18,208 +18,60 @@
 // The fully unrolled rounds are far larger than the 32 KB instruction cache; with the field multiplication out of line
 // (one shared 80-instruction body) the pass kernels shrink from 17.6k to 10k instructions and run ~4% faster (B200, 2^20 x 32 LDE).
 #define DG_MUL_CALL 1
-#include "common.cuh"
+#include "ntt_pass.cuh"
 
 namespace dg {
 
-struct PassGeom {
-    int log_t;                          // lanes per block (power of two)
-    unsigned num_tiles;                 // blockIdx.x = outer * num_tiles + tile
-    long long in_outer, in_lane, in_point;
-    long long out_outer, out_lane, out_point;
-    long long in_batch_y, out_batch_y, in_batch_z, out_batch_z;
-    int lane_major;                     // shared-memory layout: 0 = [point][lane], 1 = [lane][point] (padded)
-    int tw_on;                          // multiply output k of lane (tile*T+lane) by tw^((tile*T+lane)*k)
-    TwiddleRef tw;
-    int has_scale;
-    fe scale;
-    int coset_on;                       // input transform of the LDE: sum_f src[j + f*fold_stride] * cw^(c*(j + f*fold_stride))
-    int fold;
-    long long fold_stride;
-    TwiddleRef cw;
-    int coset_fast;                     // fold == 1: input factor from a single-level table, lane factor merged into the output twiddle
-    const fe *cw_point;                 // cw_point[e] = (w_N^in_point)^e, e < cw_point_mask + 1
-    unsigned cw_point_mask;
-    const fe *tw_full;                  // coset_fast: tw_full[coset][k * out_point + lane] = cw^(lane * (k * blowup + coset)), or null
-    long long tw_full_stride;           // elements per coset (= transform size n)
-    int log_blowup;
-    unsigned coset0;                    // first coset handled by this launch (blockIdx.y = coset - coset0)
-    const fe *roots;                    // per-stage twiddle tables of the L-point transform: W_st[j] = w_L^(j << st), back to back
-};
-
-__device__ __forceinline__ fe tw_lookup(const TwiddleRef &t, unsigned long long e) {
-    unsigned ee = (unsigned)e & t.mask;
-    fe a = t.lo[ee & ((1u << t.lo_bits) - 1u)];
-    fe b = t.hi[ee >> t.lo_bits];
-    return fe_mul(a, b);
-}
-
-// ---- pass kernel -------------------------------------------------------------------------------------------------------
-// One block transforms a tile of T lanes x L points.  The log2(L) decimation-in-frequency stages are grouped into rounds of
-// up to 4 stages that run entirely in registers on 2^rho elements per thread ("unit"); shared memory is touched only
-// between rounds.  The first round reads its operands straight from global memory and the last one writes straight back,
-// so a 1024-point sub-transform costs 2 shared-memory round trips and 2 barriers instead of 10.  Stage twiddles come from
-// per-stage compact tables W_st[j] = w_L^(j << st) (unit-stride, conflict-free) staged in shared memory.
-template <int LOG_L> struct Rounds {
-    static constexpr int R1 = LOG_L <= 4 ? LOG_L : 4;
-    static constexpr int REM = LOG_L - R1;
-    static constexpr int R2 = REM == 0 ? 0 : (REM <= 4 ? REM : (REM + 1) / 2);
-    static constexpr int R3 = REM - R2;
-};
-
-template <int LOG_L, int S0, int RHO>
-__device__ __forceinline__ void dif_regs(fe *x, const fe *s_tw, int g_lo) {
-    constexpr int L = 1 << LOG_L, R = 1 << RHO;
-    constexpr int LOG_SP = LOG_L - S0 - RHO;
-#pragma unroll
-    for (int u = 0; u < RHO; u++) {
-        const int hr = R >> (u + 1);
-        const int st = S0 + u;
-        const fe *W = s_tw + (L - (L >> st));
-#pragma unroll
-        for (int i = 0; i < R; i++) {
-            if ((i & hr) == 0) {
-                fe a = x[i], b = x[i + hr];
-                x[i] = fe_add(a, b);
-                fe d = fe_sub(a, b);
-                // in the last round (LOG_SP == 0, g_lo == 0) the twiddle index is a compile-time constant: index 0 is w^0 = 1
-                if (st != LOG_L - 1 && !(LOG_SP == 0 && (i & (hr - 1)) == 0)) d = fe_mul(d, W[g_lo + ((i & (hr - 1)) << LOG_SP)]);
-                x[i + hr] = d;
-            }
-        }
-    }
-}
-
-template <int LOG_L, bool LANE_MAJOR>
-__device__ __forceinline__ int sidx(int pos, int t, int T) {
-    constexpr int L = 1 << LOG_L;
-    constexpr int LS = L + (L >> 3) + 1;                 // padded lane stride, one pad element per 8 points
-    return LANE_MAJOR ? (t * LS + pos + (pos >> 3)) : (pos * T + t);
-}
-
-template <int LOG_L, int S0, int RHO, bool FIRST, bool LAST, bool LANE_MAJOR>
-__device__ __forceinline__ void ntt_round(const fe *__restrict__ src, fe *__restrict__ dst, fe *s_data, const fe *s_tw, const PassGeom &g,
-                                          unsigned tile, long long in_base) {
-    constexpr int L = 1 << LOG_L, R = 1 << RHO;
-    constexpr int LOG_B = LOG_L - S0, LOG_SP = LOG_B - RHO;
-    constexpr int N_GLO = 1 << LOG_SP, N_GHI = 1 << S0;
-    const int T = 1 << g.log_t;
-    const int units = (L >> RHO) * T;
-    for (int u = threadIdx.x; u < units; u += blockDim.x) {
-        int t, g_lo, g_hi;
-        if (!LANE_MAJOR || LAST) {             // lanes fastest: global accesses of neighbouring threads are contiguous across lanes
-            t = u & (T - 1);
-            const int rest = u >> g.log_t;
-            g_lo = rest & (N_GLO - 1);
-            g_hi = rest >> LOG_SP;
-        } else {                               // points fastest: contiguous rows of the last pass / conflict-free shared accesses
-            g_lo = u & (N_GLO - 1);
-            const int rest = u >> LOG_SP;
-            g_hi = rest & (N_GHI - 1);
-            t = rest >> S0;
-        }
-        const int gbase = (g_hi << LOG_B) + g_lo;
-        fe x[R];
-#pragma unroll
-        for (int m = 0; m < R; m++) {
-            const int pos = gbase + (m << LOG_SP);
-            if (FIRST) {
-                const long long j = in_base + (long long)t * g.in_lane + (long long)pos * g.in_point;
-                if (g.coset_fast) {
-                    // p[j] * w_N^(c*pos*in_point); the lane part w_N^(c*lane) rides on the output twiddle
-                    x[m] = fe_mul(src[j], g.cw_point[((g.coset0 + (unsigned)blockIdx.y) * (unsigned)pos) & g.cw_point_mask]);
-                } else if (g.coset_on) {
-                    // sum_f src[j + f n] w_N^(c (j + f n)) = w_N^(c j) * Horner_f(src[j + f n]; u),  u = w_N^(c n) (constant per coset)
-                    const unsigned long long c = g.coset0 + blockIdx.y;
-                    const fe u = tw_lookup(g.cw, c * (unsigned long long)g.fold_stride);
-                    fe v = src[j + (long long)(g.fold - 1) * g.fold_stride];
-                    for (int f = g.fold - 2; f >= 0; f--) v = fe_add(fe_mul(v, u), src[j + (long long)f * g.fold_stride]);
-                    x[m] = fe_mul(v, tw_lookup(g.cw, c * (unsigned long long)j));
-                } else {
-                    x[m] = src[j];
-                }
-            } else {
-                x[m] = s_data[sidx<LOG_L, LANE_MAJOR>(pos, t, T)];
-            }
-        }
-        dif_regs<LOG_L, S0, RHO>(x, s_tw, g_lo);
-#pragma unroll
-        for (int m = 0; m < R; m++) {
-            const int pos = gbase + (m << LOG_SP);
-            if (LAST) {                        // position q holds X[bitrev(q)]
-                const unsigned k = __brev((unsigned)pos) >> (32 - LOG_L);
-                fe v = x[m];
-                if (g.coset_fast && g.tw_on) {
-                    if (g.tw_full)          // streamed table in the layout of the output: one 16-byte load instead of two loads and a multiplication
-                        v = fe_mul(v, g.tw_full[(long long)(g.coset0 + blockIdx.y) * g.tw_full_stride + (long long)(tile * T + t) * g.out_lane + (long long)k * g.out_point]);
-                    else
-                        v = fe_mul(v, tw_lookup(g.cw, (unsigned long long)(tile * T + t) * (((unsigned long long)k << g.log_blowup) + g.coset0 + blockIdx.y)));
-                }
-                else if (g.tw_on) v = fe_mul(v, tw_lookup(g.tw, (unsigned long long)(tile * T + t) * k));
-                if (g.has_scale) v = fe_mul(v, g.scale);
-                dst[(long long)t * g.out_lane + (long long)k * g.out_point] = v;
-            } else {
-                s_data[sidx<LOG_L, LANE_MAJOR>(pos, t, T)] = x[m];
-            }
-        }
-    }
-}
-
-template <int LOG_L, bool LANE_MAJOR>
-__global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const fe *__restrict__ src, fe *__restrict__ dst, const PassGeom g) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int L = 1 << LOG_L;
-    typedef Rounds<LOG_L> RD;
-    fe *s_tw = reinterpret_cast<fe *>(smem_raw);          // L entries: per-stage tables back to back
-    fe *s_data = s_tw + L;
-    const int T = 1 << g.log_t;
-    const unsigned tile = blockIdx.x % g.num_tiles, outer = blockIdx.x / g.num_tiles;
-    const long long in_base = (long long)outer * g.in_outer + (long long)tile * T * g.in_lane;   // index inside the vector
-    src += (long long)blockIdx.y * g.in_batch_y + (long long)blockIdx.z * g.in_batch_z;
-    dst += (long long)blockIdx.y * g.out_batch_y + (long long)blockIdx.z * g.out_batch_z + (long long)outer * g.out_outer +
-           (long long)tile * T * g.out_lane;
-    for (int i = threadIdx.x; i < L - 1; i += blockDim.x) s_tw[i] = g.roots[i];
-    if (g.tw_full) {
-        // the streamed twiddles are consumed in the last round: start pulling this block's T*16-byte segments (one per output k) into L2 now
-        const fe *tb = g.tw_full + (long long)(g.coset0 + blockIdx.y) * g.tw_full_stride + (long long)tile * T * g.out_lane;
-        for (int k = threadIdx.x; k < L; k += blockDim.x)
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(tb + (long long)k * g.out_point));
-    }
-    __syncthreads();
-    ntt_round<LOG_L, 0, RD::R1, true, RD::R2 == 0, LANE_MAJOR>(src, dst, s_data, s_tw, g, tile, in_base);
-    if constexpr (RD::R2 > 0) {
-        __syncthreads();
-        ntt_round<LOG_L, RD::R1, RD::R2, false, RD::R3 == 0, LANE_MAJOR>(src, dst, s_data, s_tw, g, tile, in_base);
-    }
-    if constexpr (RD::R3 > 0) {
-        __syncthreads();
-        ntt_round<LOG_L, RD::R1 + RD::R2, RD::R3, false, true, LANE_MAJOR>(src, dst, s_data, s_tw, g, tile, in_base);
-    }
-}
-
-typedef void (*PassKernel)(const fe *, fe *, const PassGeom);
-template <bool LM> static PassKernel pass_kernel_t(int log_l) {
+// kernel variants (ntt_pass.cuh): RMAX stages per register round, BT threads per block; inline-multiply instantiations live in ntt_inl.cu
+PassKernel pass_kernel_inline(bool lane_major, int log_l, int rmax, int bt);       // nullptr when that combination is not instantiated
+template <bool LM, int RMAX, int BT, int MINB> static PassKernel pass_kernel_t(int log_l) {
     switch (log_l) {
-        case 1: return ntt_pass_kernel<1, LM>;  case 2: return ntt_pass_kernel<2, LM>;  case 3: return ntt_pass_kernel<3, LM>;
-        case 4: return ntt_pass_kernel<4, LM>;  case 5: return ntt_pass_kernel<5, LM>;  case 6: return ntt_pass_kernel<6, LM>;
-        case 7: return ntt_pass_kernel<7, LM>;  case 8: return ntt_pass_kernel<8, LM>;  case 9: return ntt_pass_kernel<9, LM>;
-        case 10: return ntt_pass_kernel<10, LM>;
+        case 1: return ntt_pass_kernel<1, LM, RMAX, BT, MINB, 0>;  case 2: return ntt_pass_kernel<2, LM, RMAX, BT, MINB, 0>;
+        case 3: return ntt_pass_kernel<3, LM, RMAX, BT, MINB, 0>;  case 4: return ntt_pass_kernel<4, LM, RMAX, BT, MINB, 0>;
+        case 5: return ntt_pass_kernel<5, LM, RMAX, BT, MINB, 0>;  case 6: return ntt_pass_kernel<6, LM, RMAX, BT, MINB, 0>;
+        case 7: return ntt_pass_kernel<7, LM, RMAX, BT, MINB, 0>;  case 8: return ntt_pass_kernel<8, LM, RMAX, BT, MINB, 0>;
+        case 9: return ntt_pass_kernel<9, LM, RMAX, BT, MINB, 0>;  case 10: return ntt_pass_kernel<10, LM, RMAX, BT, MINB, 0>;
     }
     throw Error(-1, "unsupported sub-transform size");
+}
+
+struct NttConfig { int rmax, bt, inl; };
+static NttConfig ntt_config() {
+    static NttConfig cfg = {0, 0, 0};
+    if (!cfg.rmax) {
+        const char *e;
+        cfg.rmax = (e = getenv("DG_NTT_RMAX")) ? atoi(e) : 4;
+        cfg.bt = (e = getenv("DG_NTT_BT")) ? atoi(e) : 256;
+        cfg.inl = (e = getenv("DG_NTT_INLINE")) ? atoi(e) : 0;
+        if (cfg.rmax < 2 || cfg.rmax > 4) cfg.rmax = 4;
+        if (cfg.bt != 512) cfg.bt = 256;
+    }
+    return cfg;
 }
 
 static void launch_pass(Context &c, int log_l, PassGeom g, const fe *src, fe *dst, unsigned blocks_x, unsigned by, unsigned bz) {
     const int L = 1 << log_l, T = 1 << g.log_t;
     const size_t data = g.lane_major ? (size_t)T * (L + (L >> 3) + 1) : (size_t)L * T;
     const size_t smem = ((size_t)L + data) * sizeof(fe);
-    int threads = L * T / 16;
-    if (threads > 256) threads = 256;
+    const NttConfig cfg = ntt_config();
+    int rmax = cfg.rmax, bt = cfg.bt;
+    PassKernel k = nullptr;
+    if (cfg.inl) k = pass_kernel_inline(g.lane_major != 0, log_l, rmax, bt);
+    if (!k) {
+        const bool lm = g.lane_major != 0;
+        if (rmax == 4) { bt = 256; k = lm ? pass_kernel_t<true, 4, 256, 2>(log_l) : pass_kernel_t<false, 4, 256, 2>(log_l); }
+        else if (rmax == 3 && bt == 512) k = lm ? pass_kernel_t<true, 3, 512, 2>(log_l) : pass_kernel_t<false, 3, 512, 2>(log_l);
+        else if (rmax == 3) k = lm ? pass_kernel_t<true, 3, 256, 3>(log_l) : pass_kernel_t<false, 3, 256, 3>(log_l);
+        else if (bt == 512) k = lm ? pass_kernel_t<true, 2, 512, 2>(log_l) : pass_kernel_t<false, 2, 512, 2>(log_l);
+        else k = lm ? pass_kernel_t<true, 2, 256, 4>(log_l) : pass_kernel_t<false, 2, 256, 4>(log_l);
+    }
+    int threads = (L * T) >> (log_l < rmax ? log_l : rmax);           // one unit per thread in the largest round
+    if (threads > bt) threads = bt;
     if (threads < 32) threads = 32;
-    PassKernel k = g.lane_major ? pass_kernel_t<true>(log_l) : pass_kernel_t<false>(log_l);
-    static bool attr_set[2][MAX_LOG_L + 1] = {{false}};
-    if (!attr_set[g.lane_major][log_l]) {
+    static std::map<PassKernel, bool> attr_set;
+    if (!attr_set[k]) {
         DG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set[g.lane_major][log_l] = true;
+        attr_set[k] = true;
     }
     DG_REQUIRE(by <= 65535 && bz <= 65535, "batch too large for one launch");
     k<<<dim3(blocks_x, by, bz), threads, smem, c.stream>>>(src, dst, g); c.launches++;

@@ -25,6 +25,9 @@ struct ProveResult {
 
 extern "C" {
 
+// host threads used by the prover / FFTs (1 = the reference's behaviour; see fft::host_threads).  Returns the value in effect.
+int or_set_threads(int t) { if (t >= 1) fft::host_threads() = t; return fft::host_threads(); }
+
 // ---- field -------------------------------------------------------------------------------------------------
 void or_field_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out) {
     u128 x = ld(a), y = b ? ld(b) : 0, r = 0;

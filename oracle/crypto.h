@@ -177,8 +177,17 @@ static inline std::vector<Digest> build_merkle_nodes(const std::vector<Digest> &
     size_t n = leaves.size() / 2;
     std::vector<Digest> nodes(2 * n);
     nodes[0].fill(0);
+    const int T = fft::host_threads();
+    #pragma omp parallel for num_threads(T) if (T > 1 && n >= 4096)
     for (size_t i = 0; i < n; i++) hash(leaves[2 * i].data(), 64, nodes[n + i].data());  // leaves are contiguous 32-byte arrays
-    for (size_t i = n - 1; i >= 1; i--) hash(nodes[2 * i].data(), 64, nodes[i].data());
+    if (T <= 1) {
+        for (size_t i = n - 1; i >= 1; i--) hash(nodes[2 * i].data(), 64, nodes[i].data());
+    } else {                                                 // same nodes, level by level (a level only reads the one below it)
+        for (size_t m = n / 2; m >= 1; m >>= 1) {
+            #pragma omp parallel for num_threads(T) if (m >= 4096)
+            for (size_t i = m; i < 2 * m; i++) hash(nodes[2 * i].data(), 64, nodes[i].data());
+        }
+    }
     return nodes;
 }
 

@@ -200,6 +200,11 @@ namespace fft {
 
 static const size_t MAX_LOOP = 256;  // fft.rs:7
 
+// Optional host threading (or_set_threads).  The reference's prover passes num_threads = 1 to every FFT / batch call, so 1 is the
+// faithful default; with T > 1 the same butterflies run in OpenMP tasks (independent sub-transforms, chunked twiddle loops) and
+// the column / row / step loops of the prover are split over threads.  Every value is identical for any T.
+inline int &host_threads() { static int t = 1; return t; }
+
 static inline void butterfly(u128 *v, size_t offset, size_t stride) {
     size_t i = offset, j = offset + stride;
     u128 t = v[i];
@@ -232,6 +237,40 @@ static void fft_in_place(u128 *values, size_t len, const u128 *twiddles, size_t 
         if (i == 0) continue;
         for (size_t j = o; j < o + count; j++) butterfly_twiddle(values, twiddles[i], j, stride);
     }
+}
+
+// task-parallel form of fft_in_place: the two half-size sub-transforms of the `else` branch are independent tasks, the twiddle loop
+// of a large level is cut into chunks.  Must be called inside an OpenMP parallel region (see fft_in_place_mt).
+static void fft_in_place_tasks(u128 *values, size_t len, const u128 *twiddles, size_t count, size_t stride, size_t offset) {
+    size_t size = len / stride;
+    if (size * count <= ((size_t)1 << 14)) { fft_in_place(values, len, twiddles, count, stride, offset); return; }   // elements below this call
+    if (stride == count && count < MAX_LOOP) {
+        fft_in_place_tasks(values, len, twiddles, 2 * count, 2 * stride, offset);
+    } else {
+        #pragma omp task default(shared)
+        fft_in_place_tasks(values, len, twiddles, count, 2 * stride, offset);
+        #pragma omp task default(shared)
+        fft_in_place_tasks(values, len, twiddles, count, 2 * stride, offset + stride);
+        #pragma omp taskwait
+    }
+    for (size_t o = offset; o < offset + count; o++) butterfly(values, o, stride);
+    const size_t groups = size / 2;                      // group i covers offsets [offset + 2 i stride, .. + count)
+    const size_t chunk = std::max<size_t>(1, 4096 / count);
+    #pragma omp taskloop default(shared) grainsize(1)
+    for (size_t c0 = 1; c0 < groups; c0 += chunk) {
+        const size_t c1 = std::min(groups, c0 + chunk);
+        for (size_t i = c0; i < c1; i++) {
+            const size_t o = offset + 2 * i * stride;
+            for (size_t j = o; j < o + count; j++) butterfly_twiddle(values, twiddles[i], j, stride);
+        }
+    }
+}
+static inline void fft_in_place_mt(u128 *values, size_t len, const u128 *twiddles) {
+    const int T = host_threads();
+    if (T <= 1 || len < ((size_t)1 << 15)) { fft_in_place(values, len, twiddles, 1, 1, 0); return; }
+    #pragma omp parallel num_threads(T)
+    #pragma omp single
+    fft_in_place_tasks(values, len, twiddles, 1, 1, 0);
 }
 
 static inline size_t permute_index(size_t size, size_t index) {
@@ -276,12 +315,12 @@ static inline u128 eval(const std::vector<u128> &p, u128 x) { return eval(p.data
 
 // polynom.rs:34-41
 static inline void eval_fft_twiddles(u128 *p, size_t n, const u128 *twiddles, bool unpermute) {
-    fft::fft_in_place(p, n, twiddles, 1, 1, 0);
+    fft::fft_in_place_mt(p, n, twiddles);
     if (unpermute) fft::permute(p, n);
 }
 // polynom.rs:93-103
 static inline void interpolate_fft_twiddles(u128 *v, size_t n, const u128 *inv_twiddles, bool unpermute) {
-    fft::fft_in_place(v, n, inv_twiddles, 1, 1, 0);
+    fft::fft_in_place_mt(v, n, inv_twiddles);
     u128 inv_len = field::inv((u128)n);
     for (size_t i = 0; i < n; i++) v[i] = field::mul(v[i], inv_len);
     if (unpermute) fft::permute(v, n);
@@ -406,6 +445,8 @@ static inline u128 eval(const u128 *p, u128 x) {
 // quartic.rs:20-31
 static inline std::vector<u128> evaluate_batch(const std::vector<Q> &polys, u128 x) {
     std::vector<u128> r(polys.size());
+    const int T = fft::host_threads();
+    #pragma omp parallel for num_threads(T) if (T > 1 && polys.size() >= 4096)
     for (size_t i = 0; i < polys.size(); i++) r[i] = eval(polys[i].v, x);
     return r;
 }
@@ -415,7 +456,10 @@ static inline std::vector<Q> interpolate_batch(const std::vector<Q> &xs_all, con
     size_t n = xs_all.size();
     std::vector<Q> equations(n * 4);
     std::vector<u128> inverses(n * 4);
-    for (size_t i = 0, j = 0; i < n; i++, j += 4) {
+    const int T = fft::host_threads();
+    #pragma omp parallel for num_threads(T) if (T > 1 && n >= 4096)
+    for (size_t i = 0; i < n; i++) {
+        const size_t j = 4 * i;
         const u128 *xs = xs_all[i].v;
         u128 x01 = mul(xs[0], xs[1]), x02 = mul(xs[0], xs[2]), x03 = mul(xs[0], xs[3]);
         u128 x12 = mul(xs[1], xs[2]), x13 = mul(xs[1], xs[3]), x23 = mul(xs[2], xs[3]);
@@ -428,9 +472,19 @@ static inline std::vector<Q> interpolate_batch(const std::vector<Q> &xs_all, con
         equations[j + 3] = {{ mul(neg(x01), xs[2]), add(add(x01, x02), x12), sub(sub(neg(xs[0]), xs[1]), xs[2]), 1 }};
         inverses[j + 3]  = eval(equations[j + 3].v, xs[3]);
     }
-    inverses = inv_many(inverses);
+    if (T > 1 && n >= 4096) {                            // Montgomery's trick per chunk: the same (exact) inverses as one global batch
+        const size_t total = n * 4, chunk = (total + (size_t)T * 4 - 1) / ((size_t)T * 4);
+        std::vector<u128> out(total);
+        #pragma omp parallel for num_threads(T)
+        for (size_t c0 = 0; c0 < total; c0 += chunk) inv_many_fill(inverses.data() + c0, out.data() + c0, std::min(chunk, total - c0));
+        inverses.swap(out);
+    } else {
+        inverses = inv_many(inverses);
+    }
     std::vector<Q> result(n);
-    for (size_t i = 0, j = 0; i < n; i++, j += 4) {
+    #pragma omp parallel for num_threads(T) if (T > 1 && n >= 4096)
+    for (size_t i = 0; i < n; i++) {
+        const size_t j = 4 * i;
         const u128 *ys = ys_all[i].v;
         u128 inv_y = mul(ys[0], inverses[j]);
         for (int k = 0; k < 4; k++) result[i].v[k] = mul(inv_y, equations[j].v[k]);

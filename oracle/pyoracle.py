@@ -33,6 +33,8 @@ def lib():
         L.or_result_free.argtypes = [ctypes.c_void_p]
         L.or_verify.restype = ctypes.c_int
         L.or_verify.argtypes = [u8p, u8p, ctypes.c_uint32, u8p, ctypes.c_uint32, u8p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint32]
+        L.or_set_threads.restype = ctypes.c_int
+        L.or_set_threads.argtypes = [ctypes.c_int]
         L.or_field_op.argtypes = [ctypes.c_int, u8p, u8p, u8p]
         L.or_root_of_unity.argtypes = [ctypes.c_uint64, u8p]
         L.or_inv_many.argtypes = [u8p, u8p, ctypes.c_uint64]
@@ -83,6 +85,11 @@ def lib():
 
 HASH_IDS = {"blake3": 0, "rescue": 1, "poseidon": 2, "gmimc": 3}
 _MASK = 2**64 - 1
+
+
+def set_threads(t):
+    """Host threads of the oracle prover (1 = single thread, what the reference does: every FFT / batch call gets num_threads = 1)."""
+    return lib().or_set_threads(int(t))
 
 
 def _f(v):

@@ -175,6 +175,8 @@ static const size_t MAX_REMAINDER_LENGTH = 256;
 
 static inline std::vector<Digest> hash_values(const std::vector<quartic::Q> &values, HashFn hash) {
     std::vector<Digest> r(values.size());
+    const int T = fft::host_threads();
+    #pragma omp parallel for num_threads(T) if (T > 1 && values.size() >= 4096)
     for (size_t i = 0; i < values.size(); i++) hash((const uint8_t *)values[i].v, 64, r[i].data());
     return r;
 }
@@ -277,18 +279,35 @@ static inline StarkProof prove(const std::vector<std::vector<u128>> &registers, 
     std::vector<u128> inv_twiddles = fft::get_inv_twiddles(trace_root_w, n);
     std::vector<std::vector<u128>> polys(registers);
     std::vector<std::vector<u128>> ext(w);
-    for (size_t j = 0; j < w; j++) {
-        polynom::interpolate_fft_twiddles(polys[j].data(), n, inv_twiddles.data(), true);
-        ext[j].assign(N, 0);
-        std::copy(polys[j].begin(), polys[j].end(), ext[j].begin());
-        polynom::eval_fft_twiddles(ext[j].data(), N, lde_twiddles.data(), true);
+    const int T = fft::host_threads();
+    if (T <= 1 || (size_t)T >= 2 * w) {                  // many more threads than columns: parallelism inside each transform instead
+        for (size_t j = 0; j < w; j++) {
+            polynom::interpolate_fft_twiddles(polys[j].data(), n, inv_twiddles.data(), true);
+            ext[j].assign(N, 0);
+            std::copy(polys[j].begin(), polys[j].end(), ext[j].begin());
+            polynom::eval_fft_twiddles(ext[j].data(), N, lde_twiddles.data(), true);
+        }
+    } else {                                                 // one column per thread, each transform sequential as in the reference
+        #pragma omp parallel for schedule(dynamic) num_threads(T)
+        for (size_t j = 0; j < w; j++) {
+            fft::fft_in_place(polys[j].data(), n, inv_twiddles.data(), 1, 1, 0);
+            const u128 inv_len = field::inv((u128)n);
+            for (size_t i = 0; i < n; i++) polys[j][i] = field::mul(polys[j][i], inv_len);
+            fft::permute(polys[j].data(), n);
+            ext[j].assign(N, 0);
+            std::copy(polys[j].begin(), polys[j].end(), ext[j].begin());
+            fft::fft_in_place(ext[j].data(), N, lde_twiddles.data(), 1, 1, 0);
+            fft::permute(ext[j].data(), N);
+        }
     }
     double t1 = now_ms(); if (dbg) dbg->stage_ms[0] = t1 - t0;
 
     // 2 ----- trace Merkle tree (trace_table.rs:174-185) ------------------------------------------
     std::vector<Digest> hashed_states(N);
+    #pragma omp parallel num_threads(T) if (T > 1)
     {
         std::vector<u128> row(w);
+        #pragma omp for
         for (size_t i = 0; i < N; i++) {
             for (size_t j = 0; j < w; j++) row[j] = ext[j][i];
             hash((const uint8_t *)row.data(), w * 16, hashed_states[i].data());
@@ -305,15 +324,27 @@ static inline StarkProof prove(const std::vector<std::vector<u128>> &registers, 
                         last_state.sponge, last_state.op_counter, inputs, outputs);
     std::vector<u128> i_ev(E), f_ev(E), t_ev(E);
     {
-        TraceState cur(ctx_depth, loop_depth, stack_depth), nxt(ctx_depth, loop_depth, stack_depth);
-        size_t stride = b / MAX_CONSTRAINT_DEGREE;
-        for (size_t i = 0; i < N; i += stride) {
-            cur.from_columns(ext, i);
-            nxt.from_columns(ext, (i + b) % N);
-            size_t step = i / stride;
-            evaluator.evaluate_boundaries(cur, lde_domain[i], i_ev[step], f_ev[step]);
-            t_ev[step] = evaluator.evaluate_transition(cur, nxt, lde_domain[i], step);
+        const size_t stride = b / MAX_CONSTRAINT_DEGREE;
+        std::string failure;                                 // first (lowest-step) failure, reported as the sequential loop would
+        size_t failure_step = ~(size_t)0;
+        #pragma omp parallel num_threads(T) if (T > 1)
+        {
+            TraceState cur(ctx_depth, loop_depth, stack_depth), nxt(ctx_depth, loop_depth, stack_depth);
+            #pragma omp for schedule(static)
+            for (size_t step = 0; step < E; step++) {
+                const size_t i = step * stride;
+                try {
+                    cur.from_columns(ext, i);
+                    nxt.from_columns(ext, (i + b) % N);
+                    evaluator.evaluate_boundaries(cur, lde_domain[i], i_ev[step], f_ev[step]);
+                    t_ev[step] = evaluator.evaluate_transition(cur, nxt, lde_domain[i], step);
+                } catch (const std::exception &e) {
+                    #pragma omp critical
+                    if (step < failure_step) { failure_step = step; failure = e.what(); }
+                }
+            }
         }
+        if (failure_step != ~(size_t)0) throw std::runtime_error(failure);
     }
     if (dbg) { dbg->i_evals = i_ev; dbg->f_evals = f_ev; dbg->t_evals = t_ev; }
     double t3 = now_ms(); if (dbg) dbg->stage_ms[2] = t3 - t2;

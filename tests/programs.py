@@ -21,6 +21,33 @@ def merkle_example(depth, po):
     return hostvm.execute(hostvm.merkle_program(depth, leaf_index), secret_a=a, secret_b=b, num_outputs=4)
 
 
+def merkle_paths(depth, count, po):
+    """`count` Merkle authentication paths of length `depth` verified back to back with the program of examples/merkle.rs:41-57
+    (smpath then pmpath, both Rescue-based); seeds follow the example's, with the path number in byte 3.  The example itself cannot
+    reach BASELINE's 2^14 steps: its index arithmetic (`usize::pow(2, n - 1)`, examples/merkle.rs:75,106) caps the depth at 64
+    (2^12 steps), and pmpath's binary decomposition needs 2^(depth-1) < M.  Four depth-64 paths give the 2^14-step, Rescue-dominated
+    trace that config names."""
+    a_all, b_all, blocks = [], [], []
+    for c in range(count):
+        s1 = bytes([1, 2, 3, c] + [0] * 28)
+        s2 = bytes([4, 5, 6, c] + [0] * 28)
+        p0, p1 = po.prng_vector(s1, depth), po.prng_vector(s2, depth)
+        leaf_index = p0[0] % (2 ** (depth - 1))
+        a, b = [p0[0]], [p1[0]]
+        index = leaf_index + 2 ** (depth - 1)
+        for i in range(1, depth):
+            a += [0, p0[i]]
+            b += [index & 1, p1[i]]
+            index >>= 1
+        for i in range(1, depth):
+            a.append(p0[i])
+            b.append(p1[i])
+        a_all += a
+        b_all += b
+        blocks.append(f"read.ab dup.2 smpath.{depth} swap.2 push.{leaf_index} roll.4 swap swap.2 pmpath.{depth}")
+    return hostvm.execute("begin " + " drop.4 ".join(blocks) + " end", secret_a=a_all, secret_b=b_all, num_outputs=4)
+
+
 def small_programs():
     """name -> ExecutionTrace ; all have 2^6..2^9 steps so the CPU oracle proves each in well under a second"""
     P = {}

@@ -108,3 +108,18 @@ def test_fri_round_trip_reference_tests(po):
     ev2 = evaluations(512, 64, 12)
     assert run(ev2, 63) == (1, "remainder is not a valid degree 15 polynomial")
     assert run(ev2, 63, drop=1) == (1, "evaluations did not match column value at depth 0")
+
+
+def test_threads_do_not_change_the_proof(po):
+    """the optional host threading of the oracle (or_set_threads) only re-partitions exact field arithmetic: identical bytes"""
+    from distaff_b200 import hostvm
+    tr = hostvm.collatz(7)                      # 4096 steps: large enough for the threaded FFT / Merkle / batch-inversion paths
+    po.set_threads(1)
+    a = po.prove(tr.registers, tr.ctx_depth, tr.loop_depth, tr.public_inputs, tr.outputs)
+    try:
+        po.set_threads(4)
+        b = po.prove(tr.registers, tr.ctx_depth, tr.loop_depth, tr.public_inputs, tr.outputs)
+    finally:
+        po.set_threads(1)
+    assert a.error is None and b.error is None
+    assert a.proof == b.proof
