@@ -944,7 +944,7 @@ void launch_constraint_eval(Context &c, const AirParams &P) {
     air_upload_constants();
     const unsigned long long E = (unsigned long long)P.num_c8 << P.log_n;
     static int variant = -1;
-    if (variant < 0) { const char *e = getenv("DG_AIR_CFG"); variant = e ? atoi(e) : 5; }
+    if (variant < 0) { const char *e = getenv("DG_AIR_CFG"); variant = e ? atoi(e) : 6; }
 #define DG_AIR_LAUNCH(BLOCK, MINB) constraint_eval_kernel<BLOCK, MINB><<<(unsigned)((E + BLOCK - 1) / BLOCK), BLOCK, 0, c.stream>>>(P)
 #define DG_AIR_LAUNCH_SMEM(BLOCK, MINB, DEC)                                                                                         \
     do {                                                                                                                             \
@@ -958,7 +958,9 @@ void launch_constraint_eval(Context &c, const AirParams &P) {
     const unsigned long long n = 1ULL << P.log_n;
     // the shared-memory variants need whole blocks inside one coset and at most ~200 KB of rows per block
     if (v >= 5 && (n < 128 || (size_t)P.w * 129 * sizeof(fe) > 200 * 1024)) v = 1;
-    switch (v) {                      // B200, 2^20 steps (r01): (128, 4) 21.6 ms, (256, 2) 22.3 ms, (256, 1) 28.1 ms
+    // B200, 2^20 steps x 26 registers: per-thread arrays (r01) (128, 4) 20.9 ms, (256, 2) 22.3, (256, 1) 28.1;
+    // shared-memory rows (r02): stack-like columns only (128, 4) 19.9 / (128, 3) 21.3; all columns (128, 4) 19.1 / (128, 3) 20.6
+    switch (v) {
         case 2: DG_AIR_LAUNCH(256, 2); break;
         case 4: DG_AIR_LAUNCH(256, 1); break;
         case 5: DG_AIR_LAUNCH_SMEM(128, 4, false); break;

@@ -118,6 +118,17 @@ struct Context {
     size_t small_root_offset[16];
     std::map<int, TwiddleTable> twiddles;   // key = log_order * 2 + inverse
     DevBuf ntt_tmp;
+    struct PinnedBuf {                       // page-locked host memory owned by the library (staging of pageable traces)
+        void *p = nullptr; size_t bytes = 0;
+        void ensure(size_t n) {
+            if (bytes >= n) return;
+            if (p) cudaFreeHost(p);
+            p = nullptr; bytes = 0;
+            DG_CUDA(cudaHostAlloc(&p, n, cudaHostAllocDefault));
+            bytes = n;
+        }
+    } staging;
+    cudaStream_t staging_streams[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf upload_buf;                       // device copy of a host trace (dg_prove), kept between proofs                         // scratch of the multi-pass transforms
     std::string last_error;
     unsigned long long launches = 0;        // kernels launched by this library (bench.py's gpu_launches)

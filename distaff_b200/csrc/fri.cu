@@ -63,6 +63,61 @@ void fri_fold(Context &c, const fe *values, Layout in, fe *next, Layout out, fe 
     DG_CUDA(cudaGetLastError());
 }
 
+// ---- coset-sharded layers (multi-GPU): a rank holds the cosets [c0, c0 + 2^log_nc) of a layer of 2^log_d values as the slab
+//      [c - c0][k], k < 2^(log_d - log_b).  Row r = b k' + c and its three companions r + jR (R = D/4) have k = k' + j R/b inside the
+//      same coset, so hashing and folding need no other rank's data; the folded value of row r is element k' of coset c of the next layer.
+__global__ void __launch_bounds__(256) fri_hash_rows_local_kernel(const fe *__restrict__ v, int log_d, int log_b, int log_nc, uint4 *__restrict__ items) {
+    const int log_kr = log_d - 2 - log_b;                       // rows per coset
+    const unsigned long long total = 1ULL << (log_kr + log_nc);
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const unsigned long long cl = t >> log_kr, kp = t & ((1ULL << log_kr) - 1ULL);
+    const uint4 *col = reinterpret_cast<const uint4 *>(v) + (cl << (log_d - log_b)) + kp;
+    uint32_t m[16], cv[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint4 x = col[(unsigned long long)j << log_kr];
+        m[4 * j] = x.x; m[4 * j + 1] = x.y; m[4 * j + 2] = x.z; m[4 * j + 3] = x.w;
+    }
+    b3::hash64(m, cv);
+    const unsigned long long it = (kp << log_nc) + cl;        // ShardedTree item layout [k'][c - c0]
+    items[2 * it] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    items[2 * it + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+void fri_hash_rows_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, void *items_local) {
+    const unsigned long long total = 1ULL << (log_d - 2 - log_b + log_nc);
+    fri_hash_rows_local_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(values_local, log_d, log_b, log_nc, (uint4 *)items_local); c.launches++;
+    DG_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) fri_fold_local_kernel(const fe *__restrict__ v, int log_d, int log_b, int log_nc, unsigned c0, fe *__restrict__ next,
+                                                             fe alpha, TwiddleRef inv_root, int shift, fe tau_inv, fe inv4) {
+    const int log_kr = log_d - 2 - log_b;
+    const unsigned long long total = 1ULL << (log_kr + log_nc);
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const unsigned long long cl = t >> log_kr, kp = t & ((1ULL << log_kr) - 1ULL);
+    const fe *col = v + (cl << (log_d - log_b)) + kp;
+    const fe y0 = col[0], y1 = col[1ULL << log_kr], y2 = col[2ULL << log_kr], y3 = col[3ULL << log_kr];
+    const unsigned long long r = (kp << log_b) + c0 + cl;
+    const unsigned ee = (unsigned)((r << shift) & (unsigned long long)inv_root.mask);
+    fe xinv = fe_mul(inv_root.lo[ee & ((1u << inv_root.lo_bits) - 1u)], inv_root.hi[ee >> inv_root.lo_bits]);
+    fe u = fe_mul(alpha, xinv);
+    fe s02 = fe_add(y0, y2), d02 = fe_sub(y0, y2), s13 = fe_add(y1, y3), d13 = fe_mul(fe_sub(y1, y3), tau_inv);
+    fe a0 = fe_add(s02, s13), a1 = fe_add(d02, d13), a2 = fe_sub(s02, s13), a3 = fe_sub(d02, d13);
+    fe acc = fe_add(a2, fe_mul(u, a3));
+    acc = fe_add(a1, fe_mul(u, acc));
+    acc = fe_add(a0, fe_mul(u, acc));
+    next[t] = fe_mul(acc, inv4);                               // [c - c0][k'] of the next layer
+}
+void fri_fold_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, unsigned c0, fe *next_local, fe alpha,
+                    const TwiddleRef &inv_root_table, int log_n_total, fe tau_inv, fe inv4) {
+    const unsigned long long total = 1ULL << (log_d - 2 - log_b + log_nc);
+    fri_fold_local_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(values_local, log_d, log_b, log_nc, c0, next_local, alpha, inv_root_table,
+                                                                                  log_n_total - log_d, tau_inv, inv4); c.launches++;
+    DG_CUDA(cudaGetLastError());
+}
+
 // nodes[L/2 + j] = H(ev[4j], ev[4j+1], ev[4j+2], ev[4j+3]) with L = N/2 two-element leaves (prover.rs:84-86, 180-187)
 __global__ void __launch_bounds__(256) constraint_first_level_kernel(const fe *__restrict__ ev, int log_n, int log_blowup, uint4 *__restrict__ nodes) {
     const unsigned long long n = 1ULL << log_n;

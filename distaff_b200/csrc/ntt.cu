@@ -35,16 +35,33 @@ template <bool LM, int RMAX, int BT, int MINB> static PassKernel pass_kernel_t(i
     throw Error(-1, "unsupported sub-transform size");
 }
 
-struct NttConfig { int rmax, bt, inl; };
-static NttConfig ntt_config() {
-    static NttConfig cfg = {0, 0, 0};
-    if (!cfg.rmax) {
-        const char *e;
-        cfg.rmax = (e = getenv("DG_NTT_RMAX")) ? atoi(e) : 4;
-        cfg.bt = (e = getenv("DG_NTT_BT")) ? atoi(e) : 256;
-        cfg.inl = (e = getenv("DG_NTT_INLINE")) ? atoi(e) : 0;
-        if (cfg.rmax < 2 || cfg.rmax > 4) cfg.rmax = 4;
-        if (cfg.bt != 512) cfg.bt = 256;
+// Kernel configuration per pass kind: A = strided passes (first / middle), B = the contiguous last pass; "f" variants are used by the
+// transforms whose first pass folds 8 coefficient blocks (constraint / composition LDE).  B200, 2^20 x 32 LDE of 26 columns (r02):
+//   out-of-line multiply, 16-element units, 256 threads (r01)   57.8 ms
+//   out-of-line, 4-element units, 512 threads                   53.3 ms      (32 instead of 16 resident warps per SM)
+//   inline multiply, 8-element units, 512 threads               51.8 ms      inline, 4-element units, 512 threads: 52.7 ms
+//   inline, 256 threads (8 / 4-element units)                   61.2 / 58.7 ms
+// Environment overrides (read once): DG_NTT_A / DG_NTT_B / DG_NTT_AF = "rmax,threads,inline", DG_NTT_TILE = log2 of the tile size.
+struct PassCfg { int rmax, bt, inl; };
+struct NttConfig { PassCfg a, b, af; int tile_log; };
+static PassCfg parse_cfg(const char *env, PassCfg d) {
+    const char *e = getenv(env);
+    if (e) { int r = 0, t = 0, i = 0; if (sscanf(e, "%d,%d,%d", &r, &t, &i) == 3) d = PassCfg{r, t, i}; }
+    if (d.rmax < 2 || d.rmax > 4) d.rmax = 4;
+    if (d.bt != 512 && d.bt != 1024) d.bt = 256;
+    return d;
+}
+static const NttConfig &ntt_config() {
+    static NttConfig cfg;
+    static bool init = false;
+    if (!init) {
+        cfg.a = parse_cfg("DG_NTT_A", PassCfg{3, 512, 1});
+        cfg.b = parse_cfg("DG_NTT_B", PassCfg{3, 512, 1});
+        cfg.af = parse_cfg("DG_NTT_AF", PassCfg{2, 512, 1});
+        const char *e = getenv("DG_NTT_TILE");
+        cfg.tile_log = e ? atoi(e) : 12;
+        if (cfg.tile_log < 12 || cfg.tile_log > 13) cfg.tile_log = 12;
+        init = true;
     }
     return cfg;
 }
@@ -53,12 +70,14 @@ static void launch_pass(Context &c, int log_l, PassGeom g, const fe *src, fe *ds
     const int L = 1 << log_l, T = 1 << g.log_t;
     const size_t data = g.lane_major ? (size_t)T * (L + (L >> 3) + 1) : (size_t)L * T;
     const size_t smem = ((size_t)L + data) * sizeof(fe);
-    const NttConfig cfg = ntt_config();
+    const NttConfig &nc = ntt_config();
+    const PassCfg cfg = g.lane_major ? nc.b : ((g.coset_on && !g.coset_fast) ? nc.af : nc.a);
     int rmax = cfg.rmax, bt = cfg.bt;
     PassKernel k = nullptr;
     if (cfg.inl) k = pass_kernel_inline(g.lane_major != 0, log_l, rmax, bt);
     if (!k) {
         const bool lm = g.lane_major != 0;
+        if (bt == 1024) bt = 512;
         if (rmax == 4) { bt = 256; k = lm ? pass_kernel_t<true, 4, 256, 2>(log_l) : pass_kernel_t<false, 4, 256, 2>(log_l); }
         else if (rmax == 3 && bt == 512) k = lm ? pass_kernel_t<true, 3, 512, 2>(log_l) : pass_kernel_t<false, 3, 512, 2>(log_l);
         else if (rmax == 3) k = lm ? pass_kernel_t<true, 3, 256, 3>(log_l) : pass_kernel_t<false, 3, 256, 3>(log_l);
@@ -70,7 +89,7 @@ static void launch_pass(Context &c, int log_l, PassGeom g, const fe *src, fe *ds
     if (threads < 32) threads = 32;
     static std::map<PassKernel, bool> attr_set;
     if (!attr_set[k]) {
-        DG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        DG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[k] = true;
     }
     DG_REQUIRE(by <= 65535 && bz <= 65535, "batch too large for one launch");
@@ -80,7 +99,8 @@ static void launch_pass(Context &c, int log_l, PassGeom g, const fe *src, fe *ds
 
 static int lanes_log(int log_l, long long available) {
     int lt = 4;                                   // 16 lanes
-    while ((1 << (log_l + lt)) > 4096 && lt > 0) lt--;    // keep tiles at 4096 elements = 64 KB
+    const int tile = 1 << ntt_config().tile_log;
+    while ((1 << (log_l + lt)) > tile && lt > 0) lt--;    // keep tiles at 4096 elements = 64 KB (8192 with DG_NTT_TILE=13)
     while ((1LL << lt) > available && lt > 0) lt--;
     return lt;
 }

@@ -15,6 +15,7 @@ template <bool LM, int RMAX, int BT, int MINB> static PassKernel inl_t(int log_l
 }
 
 PassKernel pass_kernel_inline(bool lm, int log_l, int rmax, int bt) {
+    if (rmax == 3 && bt == 1024) return lm ? inl_t<true, 3, 1024, 1>(log_l) : inl_t<false, 3, 1024, 1>(log_l);
     if (rmax == 3 && bt == 512) return lm ? inl_t<true, 3, 512, 2>(log_l) : inl_t<false, 3, 512, 2>(log_l);
     if (rmax == 3) return lm ? inl_t<true, 3, 256, 3>(log_l) : inl_t<false, 3, 256, 3>(log_l);
     if (rmax == 2 && bt == 512) return lm ? inl_t<true, 2, 512, 2>(log_l) : inl_t<false, 2, 512, 2>(log_l);

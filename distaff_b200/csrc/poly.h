@@ -55,6 +55,10 @@ void fri_hash_rows(Context &c, const fe *values, Layout in, Layout rows, void *l
 // next[r] = f_r(alpha), f_r = cubic through (x_r t^j, v[r + jR])   (fri/prover.rs:26-32, quartic.rs:20-135)
 void fri_fold(Context &c, const fe *values, Layout in, fe *next, Layout out, fe alpha, const TwiddleRef &inv_root_table, int log_n_total,
               fe tau_inv, fe inv4);
+// coset-sharded variants (a rank holds cosets [c0, c0 + 2^log_nc) of the layer as [c - c0][k]); items in ShardedTree order [k'][c - c0]
+void fri_hash_rows_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, void *items_local);
+void fri_fold_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, unsigned c0, fe *next_local, fe alpha,
+                    const TwiddleRef &inv_root_table, int log_n_total, fe tau_inv, fe inv4);
 // first level of the constraint tree straight from coset-major evaluations: nodes[L/2 + j] = H(ev[4j..4j+3]), L = N/2 leaves
 void constraint_tree_first_level(Context &c, const fe *evals, int log_n, int log_blowup, void *nodes);
 

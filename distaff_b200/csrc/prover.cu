@@ -8,7 +8,9 @@
 #include "poly.h"
 #include "shard.h"
 #include <array>
+#include <atomic>
 #include <memory>
+#include <thread>
 
 namespace dg {
 
@@ -106,12 +108,101 @@ int ilog2(uint64_t v) { int l = 0; while ((1ULL << l) < v) l++; return l; }
 
 struct FriLayerDev {
     DevBuf leaves, nodes, folded;     // row hashes, tree, and the folded values (= values of the next layer)
-    const fe *vals;
-    Layout layout;                    // layout of `vals` (domain size 2^layout.log_d)
+    const fe *vals;                   // replicated layer: the whole vector; sharded layer: this rank's cosets [c - c0][k]
+    Layout layout;                    // layout of the (whole) layer (domain size 2^layout.log_d)
+    bool sharded = false;             // multi-GPU: rows hashed / folded per coset range, tree = ShardedTree over [k'][c - c0] items
+    ShardedTree tree;
     Digest root;
 };
 
 }  // namespace
+
+// Upload of a host trace, overlapped with stage 1: column chunk i is extended as soon as its copy has landed.
+//   * pinned (page-locked / registered) columns: cudaMemcpyAsync straight from the caller's memory on the copy stream;
+//   * pageable columns (what a Rust Vec<u128> is): cudaMemcpyAsync would stage them through the driver's bounce buffer at ~8 GB/s and
+//     block the calling thread (r02: 155 ms end to end instead of 104).  Instead a few worker threads memcpy columns into the
+//     library's own pinned slots and enqueue the DMA from there, so staging, DMA and the LDE of earlier columns run concurrently.
+// The destructor joins the workers and drains the copy streams: on an error path no DMA from the caller's buffers is left in flight
+// (the caller may free them as soon as dg_prove returns).
+class TraceUploader {
+public:
+    static const int WORKERS = 4, SLOTS = 2;
+    TraceUploader(Context &c, fe *d_regs, const uint8_t *const *host_cols, int w, uint64_t n, int chunk)
+        : c_(c), w_(w), chunk_(chunk), nchunks_((w + chunk - 1) / chunk), col_bytes_(n * 16), done_(nchunks_, nullptr), recorded_(nchunks_) {
+        for (auto &r : recorded_) r.store(0);
+        for (auto &e : done_) DG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        // the destination comes from the stream-ordered pool / arena of the compute stream: order the copies after it
+        cudaEvent_t ready;
+        DG_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        DG_CUDA(cudaEventRecord(ready, c.stream));
+        cudaPointerAttributes attr;
+        bool pinned = cudaPointerGetAttributes(&attr, host_cols[0]) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (getenv("DG_NO_STAGING")) pinned = true;
+        if (pinned) {
+            DG_CUDA(cudaStreamWaitEvent(c.copy_stream, ready, 0));
+            for (int i = 0; i < nchunks_; i++) {           // enqueue every upload first: the copy engine runs ahead of the compute stream
+                for (int j = i * chunk; j < std::min(w, (i + 1) * chunk); j++)
+                    DG_CUDA(cudaMemcpyAsync(d_regs + (size_t)j * n, host_cols[j], col_bytes_, cudaMemcpyHostToDevice, c.copy_stream));
+                DG_CUDA(cudaEventRecord(done_[i], c.copy_stream));
+                recorded_[i].store(1);
+            }
+        } else {
+            c.staging.ensure((size_t)WORKERS * SLOTS * col_bytes_);
+            for (int t = 0; t < WORKERS; t++) {
+                if (!c.staging_streams[t]) DG_CUDA(cudaStreamCreateWithFlags(&c.staging_streams[t], cudaStreamNonBlocking));
+                DG_CUDA(cudaStreamWaitEvent(c.staging_streams[t], ready, 0));
+            }
+            const int dev = c.device;
+            for (int t = 0; t < WORKERS; t++)
+                workers_.emplace_back([this, t, dev, d_regs, host_cols, n]() {
+                    cudaSetDevice(dev);
+                    cudaStream_t st = c_.staging_streams[t];
+                    cudaEvent_t slot_free[SLOTS] = {nullptr, nullptr};
+                    int use = 0;
+                    // worker t owns the chunks i = t, t + WORKERS, ... ; chunks complete in order per worker, the consumer waits per chunk
+                    for (int i = t; i < nchunks_ && !failed_.load(); i += WORKERS) {
+                        for (int j = i * chunk_; j < std::min(w_, (i + 1) * chunk_); j++, use++) {
+                            const int s = use % SLOTS;
+                            uint8_t *slot = (uint8_t *)c_.staging.p + ((size_t)t * SLOTS + s) * col_bytes_;
+                            if (slot_free[s]) cudaEventSynchronize(slot_free[s]);
+                            else cudaEventCreateWithFlags(&slot_free[s], cudaEventDisableTiming);
+                            memcpy(slot, host_cols[j], col_bytes_);
+                            if (cudaMemcpyAsync(d_regs + (size_t)j * n, slot, col_bytes_, cudaMemcpyHostToDevice, st) != cudaSuccess) failed_.store(true);
+                            cudaEventRecord(slot_free[s], st);
+                        }
+                        if (cudaEventRecord(done_[i], st) != cudaSuccess) failed_.store(true);
+                        recorded_[i].store(1);
+                    }
+                    for (int i = t; i < nchunks_; i += WORKERS) recorded_[i].store(1);      // after a failure: release the consumer
+                    cudaStreamSynchronize(st);
+                    for (auto &e : slot_free) if (e) cudaEventDestroy(e);
+                });
+        }
+        cudaEventDestroy(ready);
+    }
+    // makes the compute stream wait for chunk i (blocks the host only until the copy of that chunk has been enqueued)
+    void wait_chunk(int i) {
+        while (!recorded_[i].load()) std::this_thread::yield();
+        if (failed_.load()) throw Error(DG_ERR_CUDA, "host trace upload failed");
+        DG_CUDA(cudaStreamWaitEvent(c_.stream, done_[i], 0));
+    }
+    int chunks() const { return nchunks_; }
+    ~TraceUploader() {
+        failed_.store(true);                               // stops workers that have not started their next chunk (normal exit: all done)
+        for (auto &t : workers_) t.join();
+        cudaStreamSynchronize(c_.copy_stream);
+        for (auto &e : done_) if (e) cudaEventDestroy(e);
+    }
+private:
+    Context &c_;
+    int w_, chunk_, nchunks_;
+    size_t col_bytes_;
+    std::vector<cudaEvent_t> done_;
+    std::vector<std::atomic<int>> recorded_;
+    std::atomic<bool> failed_{false};
+    std::vector<std::thread> workers_;
+};
 
 // d_regs: register traces in device memory; when `host_cols` is given they are not there yet: column chunks are uploaded on the
 // copy stream while the previous chunk is being interpolated and extended (the upload hides behind the LDE)
@@ -156,33 +247,37 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
 
     // ---- 1: extend execution trace ---------------------------------------------------------------------------------------------------
     clk.mark(0);
-    DevBuf polys((size_t)w * n * 16), ext((size_t)w * N_loc * 16);
-    if (!host_cols) {
-        ntt_batch(c, d_regs, polys.as<fe>(), log_n, w, n, n, true);
-        lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
+    // G > 1: the interpolation is sharded by columns (rank g interpolates columns [g cpr, (g + 1) cpr) and only needs -- and, from a
+    // host trace, only uploads -- those registers), the polynomials are all-gathered, and every rank extends all columns on its cosets
+    const int cpr = (w + G - 1) / G;                           // columns per rank (the last rank may own fewer, or none)
+    DevBuf polys((size_t)cpr * G * n * 16), ext((size_t)w * N_loc * 16);
+    if (G == 1) {
+        if (!host_cols) {
+            ntt_batch(c, d_regs, polys.as<fe>(), log_n, w, n, n, true);
+            lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
+        } else {
+            const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>(w, ((uint64_t)1 << 25) / (n * 16)));   // ~32 MB per upload
+            TraceUploader up(c, d_regs, host_cols, w, n, chunk);
+            for (int i = 0; i < up.chunks(); i++) {
+                const int j0 = i * chunk, cols = std::min(w, j0 + chunk) - j0;
+                up.wait_chunk(i);
+                ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, cols, n, n, true);
+                lde_batch(c, polys.as<fe>() + (size_t)j0 * n, ext.as<fe>() + (size_t)j0 * N_loc, log_n, log_b, 1, cols, n, N_loc, c0, (unsigned)nc);
+            }
+        }
     } else {
-        const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>(w, ((uint64_t)1 << 25) / (n * 16)));   // ~32 MB per upload
-        std::vector<cudaEvent_t> done((w + chunk - 1) / chunk);
-        {   // the destination comes from the stream-ordered pool of the compute stream: order the copy stream after it
-            cudaEvent_t ready;
-            DG_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-            DG_CUDA(cudaEventRecord(ready, c.stream));
-            DG_CUDA(cudaStreamWaitEvent(c.copy_stream, ready, 0));
-            cudaEventDestroy(ready);
+        const int j0 = std::min(w, g * cpr), mine = std::min(w, j0 + cpr) - j0;
+        if (mine > 0) {
+            if (host_cols) {
+                TraceUploader up(c, d_regs + (size_t)j0 * n, host_cols + j0, mine, n, mine);
+                up.wait_chunk(0);
+                ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, mine, n, n, true);
+            } else {
+                ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, mine, n, n, true);
+            }
         }
-        for (size_t i = 0; i < done.size(); i++) {           // enqueue every upload first: the copy engine runs ahead of the compute stream
-            DG_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-            for (int j = (int)i * chunk; j < std::min(w, (int)(i + 1) * chunk); j++)
-                DG_CUDA(cudaMemcpyAsync(d_regs + (size_t)j * n, host_cols[j], n * 16, cudaMemcpyHostToDevice, c.copy_stream));
-            DG_CUDA(cudaEventRecord(done[i], c.copy_stream));
-        }
-        for (size_t i = 0; i < done.size(); i++) {
-            const int j0 = (int)i * chunk, cols = std::min(w, j0 + chunk) - j0;
-            DG_CUDA(cudaStreamWaitEvent(c.stream, done[i], 0));
-            ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, cols, n, n, true);
-            lde_batch(c, polys.as<fe>() + (size_t)j0 * n, ext.as<fe>() + (size_t)j0 * N_loc, log_n, log_b, 1, cols, n, N_loc, c0, (unsigned)nc);
-        }
-        for (auto &e : done) cudaEventDestroy(e);
+        comm_all_gather(c, polys.as<fe>() + (size_t)g * cpr * n, polys.p, (size_t)cpr * n * 16);       // in place
+        lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
     }
 
     // ---- 2: trace Merkle tree ----------------------------------------------------------------------------------------------------------
@@ -196,7 +291,13 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
     // ---- 3: evaluate constraints --------------------------------------------------------------------------------------------------------
     clk.mark(2);
     fe last_row[3];     // op_counter and program hash of the last trace step (evaluator.rs:73-74)
-    for (int j = 0; j < 3; j++) d2h(c, &last_row[j], d_regs + (size_t)j * n + (n - 1), 16);
+    if (host_cols) {
+        for (int j = 0; j < 3; j++) memcpy(&last_row[j], host_cols[j] + (n - 1) * 16, 16);
+    } else {
+        DevBuf d_last(48);
+        for (int j = 0; j < 3; j++) DG_CUDA(cudaMemcpyAsync((uint8_t *)d_last.p + 16 * j, d_regs + (size_t)j * n + (n - 1), 16, cudaMemcpyDeviceToDevice, c.stream));
+        d2h(c, last_row, d_last.p, 48);
+    }
     const fe op_count = last_row[0];
     const fe program_hash[2] = {last_row[1], last_row[2]};
     fs::ConstraintCoefficients cc = fs::draw_constraint_coefficients(proof->trace_root, ctx_depth, loop_depth, stack_depth, inputs, outputs,
@@ -286,7 +387,7 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
     fs::CompositionCoefficients dc = fs::draw_composition_coefficients(proof->constraint_root, w);
     const fe z = dc.z, zg = fe_mul(z, root_n);
     std::vector<fe> state1(w), state2(w);
-    DevBuf comp(E * 16), comp_ext(N * 16);
+    DevBuf comp(E * 16), comp_ext(N_loc * 16);
     {
         PowTable z_t(c, z, E + 1), zi_t(c, host_inv(z), E + 1), zg_t(c, zg, n + 1), zgi_t(c, host_inv(zg), n + 1);
         TwiddleRef g_t = c.twiddle(log_n, false);
@@ -312,31 +413,48 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         syn_div(c, combined.as<fe>(), scratch2.as<fe>(), scratch.as<fe>(), E, z_t.ref(), zi_t.ref(), c_at_z);   // (C(x) - C(z)) / (x - z)
         compose(c, t1, t2, scratch2.as<fe>(), comp.as<fe>(), n, E, 6 * n + 1, dc.t1_degree, dc.t2_degree, dc.constraints);
         debug_dump(c, "composition_poly", comp.p, E * 16);
-        if (G == 1) {
-            lde_batch(c, comp.as<fe>(), comp_ext.as<fe>(), log_n, log_b, 8, 1, E, N);
-        } else {   // extend the own cosets, then every rank gets the whole vector (rank-major == coset-major) to run FRI redundantly
-            DevBuf comp_loc(N_loc * 16);
-            lde_batch(c, comp.as<fe>(), comp_loc.as<fe>(), log_n, log_b, 8, 1, E, N_loc, c0, (unsigned)nc);
-            comm_all_gather(c, comp_loc.p, comp_ext.p, N_loc * 16);
-        }
+        // every rank extends its own cosets; the first FRI layers work on these slabs directly (no all-gather of the N evaluations)
+        lde_batch(c, comp.as<fe>(), comp_ext.as<fe>(), log_n, log_b, 8, 1, E, N_loc, c0, (unsigned)nc);
     }
 
     // ---- 7: FRI layers ---------------------------------------------------------------------------------------------------------------------------
     clk.mark(6);
     std::vector<FriLayerDev> layers;
+    DevBuf fri_gathered;                                       // multi-GPU: the first replicated layer, gathered from the ranks' slabs
     {
         TwiddleRef inv_root = c.twiddle(log_N, true);
         const fe tau_inv = host_inv(host_root_of_unity(2));
         const fe inv4 = host_inv(fe_make(4, 0));
         const fe *cur = comp_ext.as<fe>();
         Layout lay{log_N, log_b};
+        bool local = G > 1;                                    // `cur` is this rank's coset slab of the layer
         for (;;) {
             const int log_r = lay.log_d - 2;
             const uint64_t R = 1ULL << log_r;
-            const Layout rows{log_r, (lay.log_b >= 0 && log_r >= lay.log_b) ? lay.log_b : -1};
+            if (local && log_r - log_b < 6) {                  // small layer: gather it once and finish redundantly on every rank
+                fri_gathered.alloc((size_t)16 << lay.log_d);
+                comm_all_gather(c, cur, fri_gathered.p, ((size_t)16 << lay.log_d) >> log_g);     // rank-major == coset-major
+                cur = fri_gathered.as<fe>();
+                local = false;
+            }
             layers.emplace_back();
             FriLayerDev &L = layers.back();
-            L.vals = cur; L.layout = lay;
+            L.vals = cur; L.layout = lay; L.sharded = local;
+            if (local) {
+                // rows r = b k' + c of the own cosets: hashes in ShardedTree order, n' = R / b subtrees of nc leaves per rank
+                L.leaves.alloc((R >> log_g) * 32);
+                fri_hash_rows_local(c, cur, lay.log_d, log_b, log_nc, L.leaves.p);
+                L.tree.build(c, L.leaves.p, R >> log_b, log_nc);
+                L.root = L.tree.root;
+                fs::Rng rng(L.root.data());
+                const fe alpha = rng.field();
+                L.folded.alloc((R >> log_g) * 16);
+                fri_fold_local(c, cur, lay.log_d, log_b, log_nc, c0, L.folded.as<fe>(), alpha, inv_root, log_N, tau_inv, inv4);
+                cur = L.folded.as<fe>();
+                lay = Layout{log_r, log_b};
+                continue;
+            }
+            const Layout rows{log_r, (lay.log_b >= 0 && log_r >= lay.log_b) ? lay.log_b : -1};
             L.leaves.alloc(R * 32); L.nodes.alloc(R * 32);
             fri_hash_rows(c, cur, lay, rows, L.leaves.p);
             merkle_build(c, L.leaves.p, L.nodes.p, R);
@@ -372,114 +490,128 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
     clk.mark(8);
     fs::ByteWriter out;
     {
+        // Plan every opening on the host, fetch all opened values / digests in one batched pass (FetchBatch), then serialise.
         const int nq = (int)positions.size();
+        FetchBatch fb(c);
+        typedef std::vector<std::vector<size_t>> Offsets;
+        // registers the nodes of a batch-proof plan; leaf_ref / node_ref map leaf indices / heap indices to fetch references
+        auto plan_offsets = [&](const fs::BatchPlan &plan, auto leaf_ref, auto node_ref) {
+            Offsets o(plan.nodes.size());
+            for (size_t sidx = 0; sidx < plan.nodes.size(); sidx++)
+                for (auto &r : plan.nodes[sidx]) o[sidx].push_back(fb.add32(r.leaf ? leaf_ref(r.index) : node_ref(r.index)));
+            return o;
+        };
+        auto digests_at = [&](const Offsets &o) {
+            std::vector<std::vector<Digest>> v(o.size());
+            for (size_t i = 0; i < o.size(); i++)
+                for (size_t off : o[i]) v[i].push_back(fb.digest(off));
+            return v;
+        };
+
         // trace rows at the queried positions (trace_table.rs:127-134): the rank owning the position's coset reads the row
-        std::vector<fe> rows((size_t)nq * w);
-        {
-            std::vector<uint64_t> phys(nq);
-            std::vector<int> owners(nq);
-            for (int q = 0; q < nq; q++) {
-                const uint64_t cpos = positions[q] & (b - 1), k = positions[q] >> log_b;
-                owners[q] = (int)(cpos >> log_nc);
-                phys[q] = owners[q] == g ? (((cpos - c0) << log_n) + k) : 0;
+        std::vector<size_t> row_off(nq);
+        for (int q = 0; q < nq; q++) {
+            const uint64_t cpos = positions[q] & (b - 1), k = positions[q] >> log_b;
+            const int owner = (int)(cpos >> log_nc);
+            const uint64_t phys = ((cpos - (uint64_t)owner * nc) << log_n) + k;
+            for (int j = 0; j < w; j++) {
+                const size_t off = fb.add16(FetchRef{ext.as<fe>() + (size_t)j * N_loc, phys, owner});
+                if (j == 0) row_off[q] = off;
             }
-            DevBuf d_pos(nq * 8), d_rows((size_t)nq * w * 16);
-            h2d(c, d_pos.p, phys.data(), nq * 8);
-            gather_rows(c, ext.as<fe>(), w, N_loc, d_pos.as<unsigned long long>(), nq, d_rows.as<fe>());
-            std::vector<uint8_t> got = exchange_owned(c, d_rows.p, nq, (size_t)w * 16, owners);
-            memcpy(rows.data(), got.data(), got.size());
         }
         // trace tree openings: leaves are the row hashes
         fs::BatchPlan tplan = fs::plan_batch_proof(positions, N);
-        auto trace_nodes = resolve_plan(tplan, [&](const std::vector<uint64_t> &idx) { return t_tree.fetch_items(c, idx); },
-                                        [&](const std::vector<uint64_t> &idx) { return t_tree.fetch_nodes(c, idx); });
+        Offsets t_off = plan_offsets(tplan, [&](uint64_t i) { return t_tree.item_ref(i); }, [&](uint64_t h) { return t_tree.node_ref(h); });
 
-        // constraint tree openings: leaf j = evaluations (2j, 2j+1), unhashed (prover.rs:180-187)
-        auto constraint_leaves = [&](const std::vector<uint64_t> &idx) {
-            std::vector<uint64_t> phys;
-            std::vector<int> owners;
-            for (uint64_t j : idx) {
-                const uint64_t i = 2 * j, cpos = i & (b - 1), k = i >> log_b;
-                const int owner = (int)(cpos >> log_nc);
-                owners.push_back(owner);
-                const uint64_t p0 = owner == g ? (((cpos - c0) << log_n) + k) : 0;
-                phys.push_back(p0);
-                phys.push_back(owner == g ? p0 + n : 0);            // evaluation 2j+1 lives in the next coset, same k
-            }
-            std::vector<Digest> o(idx.size());
-            if (idx.empty()) return o;
-            DevBuf d_idx(phys.size() * 8), d_out(phys.size() * 16);
-            h2d(c, d_idx.p, phys.data(), phys.size() * 8);
-            gather16(c, c_ext.as<fe>(), d_idx.as<unsigned long long>(), (int)phys.size(), d_out.as<fe>());
-            std::vector<uint8_t> got = exchange_owned(c, d_out.p, idx.size(), 32, owners);
-            memcpy(o.data(), got.data(), got.size());
-            return o;
-        };
-        auto constraint_nodes = [&](const std::vector<uint64_t> &idx) {
-            // heap indices of the tree over N/2 leaves: [N/4, N/2) is the first hashed level (= level-0 items of c_tree)
-            std::vector<uint64_t> items, inner;
-            std::vector<size_t> ipos, npos;
-            for (size_t q = 0; q < idx.size(); q++) {
-                if (idx[q] >= N / 4) { items.push_back(idx[q] - N / 4); ipos.push_back(q); }
-                else { inner.push_back(idx[q]); npos.push_back(q); }
-            }
-            std::vector<Digest> o(idx.size());
-            std::vector<Digest> a = c_tree.fetch_items(c, items), bb = c_tree.fetch_nodes(c, inner);
-            for (size_t i = 0; i < a.size(); i++) o[ipos[i]] = a[i];
-            for (size_t i = 0; i < bb.size(); i++) o[npos[i]] = bb[i];
-            return o;
+        // constraint tree openings: leaf j = evaluations (2j, 2j+1), unhashed (prover.rs:180-187); evaluation 2j+1 lives in the next
+        // coset at the same k, i.e. n elements further in the owner's slab: two 16-byte units registered back to back = one 32-byte item
+        auto constraint_leaf = [&](uint64_t j) {
+            const uint64_t i = 2 * j, cpos = i & (b - 1), k = i >> log_b;
+            const int owner = (int)(cpos >> log_nc);
+            const uint64_t p0 = ((cpos - (uint64_t)owner * nc) << log_n) + k;
+            const size_t off = fb.add16(FetchRef{c_ext.as<fe>(), p0, owner});
+            fb.add16(FetchRef{c_ext.as<fe>(), p0 + n, owner});
+            return off;
         };
         std::vector<uint64_t> c_positions = fs::constraint_positions(positions);
         fs::BatchPlan cplan = fs::plan_batch_proof(c_positions, N / 2);
-        std::vector<Digest> c_values = constraint_leaves(cplan.value_leaves);
-        auto c_nodes_open = resolve_plan(cplan, constraint_leaves, constraint_nodes);
+        std::vector<size_t> cval_off;
+        for (uint64_t j : cplan.value_leaves) cval_off.push_back(constraint_leaf(j));
+        Offsets c_off(cplan.nodes.size());
+        for (size_t sidx = 0; sidx < cplan.nodes.size(); sidx++)
+            for (auto &r : cplan.nodes[sidx]) {
+                // heap indices of the tree over N/2 leaves: [N/4, N/2) is the first hashed level (= level-0 items of c_tree)
+                if (r.leaf) c_off[sidx].push_back(constraint_leaf(r.index));
+                else if (r.index >= N / 4) c_off[sidx].push_back(fb.add32(c_tree.item_ref(r.index - N / 4)));
+                else c_off[sidx].push_back(fb.add32(c_tree.node_ref(r.index)));
+            }
+
+        // FRI layers (fri/prover.rs:55-95)
+        struct LayerOpen { std::vector<uint64_t> pos; std::vector<size_t> val_off; Offsets node_off; uint8_t depth; };
+        std::vector<LayerOpen> fri_open(layers.size() - 1);
+        std::vector<uint64_t> fpos = positions;
+        for (size_t d = 0; d + 1 < layers.size(); d++) {
+            FriLayerDev &L = layers[d];
+            LayerOpen &O = fri_open[d];
+            const uint64_t D = 1ULL << L.layout.log_d, R = D / 4;
+            fpos = fs::augmented_positions(fpos, D);
+            O.pos = fpos;
+            fs::BatchPlan plan = fs::plan_batch_proof(fpos, R);
+            O.depth = plan.depth;
+            for (uint64_t p : fpos)
+                for (int j = 0; j < 4; j++) {
+                    size_t off;
+                    if (L.sharded) {
+                        const uint64_t cpos = p & (b - 1), k = (p >> log_b) + (uint64_t)j * (R >> log_b);
+                        const int owner = (int)(cpos >> log_nc);
+                        off = fb.add16(FetchRef{L.vals, ((cpos - (uint64_t)owner * nc) << (L.layout.log_d - log_b)) + k, owner});
+                    } else {
+                        off = fb.add16(FetchRef{L.vals, L.layout.phys(p + j * R), -1});
+                    }
+                    if (j == 0) O.val_off.push_back(off);
+                }
+            if (L.sharded) O.node_off = plan_offsets(plan, [&](uint64_t i) { return L.tree.item_ref(i); }, [&](uint64_t h) { return L.tree.node_ref(h); });
+            else O.node_off = plan_offsets(plan, [&](uint64_t i) { return FetchRef{L.leaves.p, i, -1}; }, [&](uint64_t h) { return FetchRef{L.nodes.p, h, -1}; });
+        }
+        std::vector<size_t> rem_off;
+        {
+            FriLayerDev &L = layers.back();
+            const uint64_t D = 1ULL << L.layout.log_d;
+            for (uint64_t i = 0; i < D; i++) rem_off.push_back(fb.add16(FetchRef{L.vals, L.layout.phys(i), -1}));   // remainder, natural order
+        }
+        fb.run();
 
         // ---- serialise (proof.rs:10-37; bincode: u64 length prefixes, arrays raw, little endian)
         out.raw(proof->trace_root, 32);
         out.u8(tplan.depth); out.u8((uint8_t)ctx_depth); out.u8((uint8_t)loop_depth); out.u8((uint8_t)stack_depth);
         out.u32((uint32_t)op_count.lo);                                               // op_count as u32 (proof.rs:62)
-        write_digest_vv(out, trace_nodes);
+        write_digest_vv(out, digests_at(t_off));
         out.u64(nq);
         for (int q = 0; q < nq; q++) {
             out.u64(w);
-            for (int j = 0; j < w; j++) out.felt(rows[(size_t)q * w + j]);
+            for (int j = 0; j < w; j++) out.felt(fb.value(row_off[q] + j));
         }
         out.raw(proof->constraint_root, 32);
-        write_digest_vec(out, c_values);
-        write_digest_vv(out, c_nodes_open);
+        out.u64(cval_off.size());
+        for (size_t off : cval_off) { Digest dgt = fb.digest(off); out.raw(dgt.data(), 32); }
+        write_digest_vv(out, digests_at(c_off));
         out.u8(cplan.depth);
         write_felt_vec(out, state1);
         write_felt_vec(out, state2);
 
-        // FRI proof (fri/prover.rs:55-95)
         out.u64(layers.size() - 1);
-        std::vector<uint64_t> fpos = positions;
         for (size_t d = 0; d + 1 < layers.size(); d++) {
-            FriLayerDev &L = layers[d];
-            const uint64_t D = 1ULL << L.layout.log_d, R = D / 4;
-            fpos = fs::augmented_positions(fpos, D);
-            fs::BatchPlan plan = fs::plan_batch_proof(fpos, R);
-            std::vector<uint64_t> phys;
-            for (uint64_t p : fpos)
-                for (int j = 0; j < 4; j++) phys.push_back(L.layout.phys(p + j * R));
-            std::vector<fe> vals = fetch16(c, L.vals, phys);
-            auto nodes = resolve_plan(plan, [&](const std::vector<uint64_t> &idx) { return fetch32(c, L.leaves.p, idx); },
-                                      [&](const std::vector<uint64_t> &idx) { return fetch32(c, L.nodes.p, idx); });
-            out.raw(L.root.data(), 32);
-            out.u64(fpos.size());
-            for (auto &v : vals) out.felt(v);
-            write_digest_vv(out, nodes);
-            out.u8(plan.depth);
+            LayerOpen &O = fri_open[d];
+            out.raw(layers[d].root.data(), 32);
+            out.u64(O.pos.size());
+            for (size_t off : O.val_off)
+                for (int j = 0; j < 4; j++) out.felt(fb.value(off + j));
+            write_digest_vv(out, digests_at(O.node_off));
+            out.u8(O.depth);
         }
-        {
-            FriLayerDev &L = layers.back();
-            const uint64_t D = 1ULL << L.layout.log_d;
-            std::vector<uint64_t> phys(D);
-            for (uint64_t i = 0; i < D; i++) phys[i] = L.layout.phys(i);     // remainder in column-major row order == natural order
-            std::vector<fe> rem = fetch16(c, L.vals, phys);
-            out.raw(L.root.data(), 32);
-            write_felt_vec(out, rem);
-        }
+        out.raw(layers.back().root.data(), 32);
+        out.u64(rem_off.size());
+        for (size_t off : rem_off) out.felt(fb.value(off));
         out.u64(proof->pow_nonce);
         out.u8((uint8_t)log_b); out.u8((uint8_t)opt.num_queries); out.u8((uint8_t)opt.grinding_factor); out.u8(0);
     }

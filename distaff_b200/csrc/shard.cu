@@ -150,6 +150,38 @@ std::vector<uint8_t> exchange_owned(Context &c, const void *d_local, size_t coun
     return out;
 }
 
+// out[t] = base_t ? ((const uint4 *)base_t)[unit_t] : 0
+__global__ void fetch_units_kernel(const unsigned long long *__restrict__ req, unsigned count, uint4 *__restrict__ out) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const uint4 *base = reinterpret_cast<const uint4 *>(req[2 * t]);
+    out[t] = base ? base[req[2 * t + 1]] : make_uint4(0, 0, 0, 0);
+}
+
+void FetchBatch::run() {
+    const size_t n = owner_.size();
+    out_.assign(n * 16, 0);
+    if (n == 0) return;
+    DevBuf d_req(n * 16), d_out(n * 16);
+    DG_CUDA(cudaMemcpyAsync(d_req.p, req_.data(), n * 16, cudaMemcpyHostToDevice, c_.stream));
+    fetch_units_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c_.stream>>>(d_req.as<unsigned long long>(), (unsigned)n, d_out.as<uint4>()); c_.launches++;
+    DG_CUDA(cudaGetLastError());
+    if (c_.world == 1) {
+        DG_CUDA(cudaMemcpyAsync(out_.data(), d_out.p, n * 16, cudaMemcpyDeviceToHost, c_.stream));
+        DG_CUDA(cudaStreamSynchronize(c_.stream));
+        return;
+    }
+    DevBuf all(n * 16 * c_.world);
+    comm_all_gather(c_, d_out.p, all.p, n * 16);
+    std::vector<uint8_t> host(n * 16 * c_.world);
+    DG_CUDA(cudaMemcpyAsync(host.data(), all.p, host.size(), cudaMemcpyDeviceToHost, c_.stream));
+    DG_CUDA(cudaStreamSynchronize(c_.stream));
+    for (size_t t = 0; t < n; t++) {
+        const int o = owner_[t] < 0 ? c_.rank : owner_[t];
+        memcpy(out_.data() + t * 16, host.data() + ((size_t)o * n + t) * 16, 16);
+    }
+}
+
 static std::vector<Digest> fetch_digests(Context &c, const void *src_local, const std::vector<ShardLocation> &loc) {
     const size_t count = loc.size();
     std::vector<Digest> out(count);
