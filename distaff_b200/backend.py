@@ -35,8 +35,17 @@ class DgStats(ctypes.Structure):
     _fields_ = [("stage_ms", ctypes.c_float * 9), ("h2d_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("kernel_launches", u64)]
 
 
+DRAW_FIELD_FN = ctypes.CFUNCTYPE(ctypes.c_int, vp, vp, u64, vp)
+DRAW_POSITIONS_FN = ctypes.CFUNCTYPE(ctypes.c_int, vp, vp, u64, u32, u32, vp)
+
+
+class DgRngCallbacks(ctypes.Structure):
+    _fields_ = [("user", vp), ("draw_field", DRAW_FIELD_FN), ("draw_positions", DRAW_POSITIONS_FN)]
+
+
 EXPORTS = {
     "dg_init": [ctypes.c_int],
+    "dg_set_rng_callbacks": [ctypes.POINTER(DgRngCallbacks)],
     "dg_device_info": [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_size_t)],
     "dg_prove": [ctypes.POINTER(DgTrace), vp, u32, vp, u32, ctypes.POINTER(DgOptions), ctypes.POINTER(vp), ctypes.POINTER(DgStats)],
     "dg_prove_device": [vp, u32, u64, u32, u32, vp, u32, vp, u32, ctypes.POINTER(DgOptions), ctypes.POINTER(vp), ctypes.POINTER(DgStats)],
@@ -100,6 +109,43 @@ def lib():
 def check(rc):
     if rc != 0:
         raise DgError(rc, lib().dg_last_error().decode(errors="replace"))
+
+
+_RNG_KEEPALIVE = None
+
+
+def set_rng_callbacks(draw_field=None, draw_positions=None):
+    """dg_set_rng_callbacks: draw_field(seed: bytes, count) -> bytes (count*16), draw_positions(seed, domain, ext, nq) -> list[int];
+    called with no arguments it restores the built-in generator.  (The binding a Rust host would use is in INTEGRATION.md.)"""
+    global _RNG_KEEPALIVE
+    if draw_field is None and draw_positions is None:
+        check(lib().dg_set_rng_callbacks(None))
+        _RNG_KEEPALIVE = None
+        return
+
+    def _field(user, seed, count, out):
+        try:
+            data = draw_field(ctypes.string_at(seed, 32), int(count))
+            ctypes.memmove(out, data, int(count) * 16)
+            return 0
+        except Exception:
+            return 1
+
+    def _positions(user, seed, domain, ext, nq, out):
+        try:
+            pos = draw_positions(ctypes.string_at(seed, 32), int(domain), int(ext), int(nq))
+            if len(pos) != nq:
+                return 1
+            arr = (ctypes.c_uint64 * nq)(*pos)
+            ctypes.memmove(out, arr, 8 * nq)
+            return 0
+        except Exception:
+            return 1
+
+    cb = DgRngCallbacks(None, DRAW_FIELD_FN(_field) if draw_field else DRAW_FIELD_FN(0),
+                        DRAW_POSITIONS_FN(_positions) if draw_positions else DRAW_POSITIONS_FN(0))
+    _RNG_KEEPALIVE = cb
+    check(lib().dg_set_rng_callbacks(ctypes.byref(cb)))
 
 
 def device_info():

@@ -325,6 +325,13 @@ int dg_prove_device(const void *d_registers, uint32_t width, uint64_t length, ui
                                                 n_outputs, *options, stats, 0.0f);
     });
 }
+int dg_set_rng_callbacks(const dg_rng_callbacks_t *callbacks) {
+    return guarded([&] {
+        if (!callbacks) { fs::set_rng_hooks(nullptr); return; }
+        fs::RngHooks h{callbacks->user, callbacks->draw_field, callbacks->draw_positions};
+        fs::set_rng_hooks(&h);
+    });
+}
 int dg_proof_serialized_len(const dg_proof_t *proof, size_t *len) {
     return guarded([&] { DG_REQUIRE(proof && len, "null argument"); *len = ((const Proof *)proof)->bytes.size(); });
 }

@@ -37,8 +37,54 @@ void fri_hash_rows(Context &c, const fe *values, Layout in, Layout rows, void *l
     DG_CUDA(cudaGetLastError());
 }
 
-__global__ void __launch_bounds__(256) fri_fold_kernel(const fe *__restrict__ v, Layout in, fe *__restrict__ next, Layout out, fe alpha,
+// special_x = field::prng(layer root) (fri/prover.rs:29) derived on the device, so that a layer's fold does not wait for a round trip
+// to the host: StdRng::from_seed(root) = ChaCha20 (64-bit block counter, stream 0), Uniform(0..M) = widening multiply of a 128-bit
+// draw by M with rejection of low halves > M - 1 -- the same steps as fs::Rng::field (host_fs.cu), which the CPU tests pin.
+__device__ __forceinline__ uint32_t rol32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+#define DG_QRD(a, b, c, d) a += b; d = rol32(d ^ a, 16); c += d; b = rol32(b ^ c, 12); a += b; d = rol32(d ^ a, 8); c += d; b = rol32(b ^ c, 7);
+__global__ void fri_alpha_kernel(const uint32_t *__restrict__ root, fe *__restrict__ alpha, uint32_t *__restrict__ root_copy) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    typedef unsigned __int128 u128;
+    uint32_t key[8];
+    for (int i = 0; i < 8; i++) { key[i] = root[i]; root_copy[i] = root[i]; }
+    uint32_t buf[16];
+    unsigned long long counter = 0;
+    int pos = 16;
+    auto next_u32 = [&]() {
+        if (pos >= 16) {
+            uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                               (uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
+            uint32_t x[16];
+            for (int i = 0; i < 16; i++) x[i] = in[i];
+            for (int r = 0; r < 10; r++) {
+                DG_QRD(x[0], x[4], x[8], x[12]) DG_QRD(x[1], x[5], x[9], x[13]) DG_QRD(x[2], x[6], x[10], x[14]) DG_QRD(x[3], x[7], x[11], x[15])
+                DG_QRD(x[0], x[5], x[10], x[15]) DG_QRD(x[1], x[6], x[11], x[12]) DG_QRD(x[2], x[7], x[8], x[13]) DG_QRD(x[3], x[4], x[9], x[14])
+            }
+            for (int i = 0; i < 16; i++) buf[i] = x[i] + in[i];
+            counter++;
+            pos = 0;
+        }
+        return buf[pos++];
+    };
+    auto next_u64 = [&]() { unsigned long long lo = next_u32(); unsigned long long hi = next_u32(); return lo | (hi << 32); };
+    const u128 Mv = ((u128)DG_M_HI << 64) | DG_M_LO;
+    for (;;) {
+        const unsigned long long v0 = next_u64(), v1 = next_u64();
+        const u128 p00 = (u128)v0 * DG_M_LO, p01 = (u128)v0 * DG_M_HI, p10 = (u128)v1 * DG_M_LO, p11 = (u128)v1 * DG_M_HI;
+        const u128 mid = (p00 >> 64) + (unsigned long long)p01 + (unsigned long long)p10;
+        const u128 lo = ((u128)(unsigned long long)mid << 64) | (unsigned long long)p00;
+        const u128 hi = p11 + (p01 >> 64) + (p10 >> 64) + (mid >> 64);
+        if (lo <= Mv - 1) { *alpha = fe_make((unsigned long long)hi, (unsigned long long)(hi >> 64)); return; }
+    }
+}
+void fri_alpha(Context &c, const void *root_dev, fe *alpha_dev, void *root_copy_dev) {
+    fri_alpha_kernel<<<1, 32, 0, c.stream>>>((const uint32_t *)root_dev, alpha_dev, (uint32_t *)root_copy_dev); c.launches++;
+    DG_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) fri_fold_kernel(const fe *__restrict__ v, Layout in, fe *__restrict__ next, Layout out, const fe *__restrict__ alpha_p,
                                                        TwiddleRef inv_root, int shift, fe tau_inv, fe inv4) {
+    const fe alpha = *alpha_p;
     const unsigned long long R = 1ULL << out.log_d;
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= R) return;
@@ -55,7 +101,7 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const fe *__restrict__ v,
     acc = fe_add(a0, fe_mul(u, acc));
     next[t] = fe_mul(acc, inv4);
 }
-void fri_fold(Context &c, const fe *values, Layout in, fe *next, Layout out, fe alpha, const TwiddleRef &inv_root_table, int log_n_total,
+void fri_fold(Context &c, const fe *values, Layout in, fe *next, Layout out, const fe *alpha, const TwiddleRef &inv_root_table, int log_n_total,
               fe tau_inv, fe inv4) {
     const unsigned long long R = 1ULL << out.log_d;
     const int shift = log_n_total - in.log_d;            // layer domain is the 4^depth-th powers of the LDE domain
@@ -91,7 +137,8 @@ void fri_hash_rows_local(Context &c, const fe *values_local, int log_d, int log_
 }
 
 __global__ void __launch_bounds__(256) fri_fold_local_kernel(const fe *__restrict__ v, int log_d, int log_b, int log_nc, unsigned c0, fe *__restrict__ next,
-                                                             fe alpha, TwiddleRef inv_root, int shift, fe tau_inv, fe inv4) {
+                                                             const fe *__restrict__ alpha_p, TwiddleRef inv_root, int shift, fe tau_inv, fe inv4) {
+    const fe alpha = *alpha_p;
     const int log_kr = log_d - 2 - log_b;
     const unsigned long long total = 1ULL << (log_kr + log_nc);
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,7 +157,7 @@ __global__ void __launch_bounds__(256) fri_fold_local_kernel(const fe *__restric
     acc = fe_add(a0, fe_mul(u, acc));
     next[t] = fe_mul(acc, inv4);                               // [c - c0][k'] of the next layer
 }
-void fri_fold_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, unsigned c0, fe *next_local, fe alpha,
+void fri_fold_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, unsigned c0, fe *next_local, const fe *alpha,
                     const TwiddleRef &inv_root_table, int log_n_total, fe tau_inv, fe inv4) {
     const unsigned long long total = 1ULL << (log_d - 2 - log_b + log_nc);
     fri_fold_local_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(values_local, log_d, log_b, log_nc, c0, next_local, alpha, inv_root_table,

@@ -124,42 +124,44 @@ __global__ void __launch_bounds__(512) merkle_top_kernel(uint4 *__restrict__ nod
     if (tid == 0) { nodes[0] = make_uint4(0, 0, 0, 0); nodes[1] = make_uint4(0, 0, 0, 0); }
 }
 
+// computes the levels count/2, count/4, ... down to and including the level with `stop` nodes (stop >= 1, a power of two) from the
+// input level `in` (count nodes) into the heap `nodes` (a level with m nodes sits at nodes[m .. 2m)).  One launch per level while a
+// level has more than 1024 nodes -- BLAKE3 is ALU-bound with long dependency chains, so the per-level kernel at full occupancy is the
+// fastest form (r02 measured a fused variant, 8 -> 4 -> 2 -> 1 nodes per thread in registers and 11 levels per launch: 104 registers,
+// 16 resident warps per SM, 2^25-leaf tree 2.4 ms instead of 1.2 ms) -- then the last <= 1024 nodes level by level inside one block.
+static void tree_levels(Context &c, const uint4 *in, uint4 *nodes, unsigned long long count, unsigned long long stop) {
+    while (count > stop) {
+        const unsigned long long m = count / 2;
+        if (stop == 1 && count <= 1024 && count >= 2 && in == nodes + 2 * count) {     // the rest of a complete tree: one block
+            merkle_top_kernel<<<1, 512, 0, c.stream>>>(nodes, (unsigned)count); c.launches++;
+            DG_CUDA(cudaGetLastError());
+            return;
+        }
+        merkle_level_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(in, nodes + 2 * m, m); c.launches++;
+        DG_CUDA(cudaGetLastError());
+        count = m;
+        in = nodes + 2 * m;
+    }
+}
+
 // leaves: L digests (L power of two >= 2); nodes: L digests (heap layout)
 void merkle_build(Context &c, const void *leaves, void *nodes, unsigned long long L) {
     DG_REQUIRE(L >= 2 && (L & (L - 1)) == 0, "number of leaves must be a power of 2 and >= 2");
     uint4 *nd = (uint4 *)nodes;
-    const uint4 *in = (const uint4 *)leaves;
-    unsigned long long m = L / 2;
-    // first level reads the leaves; afterwards each level reads the one below it inside `nodes`
-    while (true) {
-        merkle_level_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(in, nd + 2 * m, m); c.launches++;
-        DG_CUDA(cudaGetLastError());
-        if (m <= 1024) break;
-        in = nd + 2 * m;
-        m >>= 1;
-    }
-    if (m >= 2) {
-        merkle_top_kernel<<<1, 512, 0, c.stream>>>(nd, (unsigned)m); c.launches++;
-        DG_CUDA(cudaGetLastError());
-    } else {
-        DG_CUDA(cudaMemsetAsync(nd, 0, 32, c.stream));   // L == 2: nodes[1] already written, nodes[0] = 0
-    }
+    tree_levels(c, (const uint4 *)leaves, nd, L, 1);
+    DG_CUDA(cudaMemsetAsync(nd, 0, 32, c.stream));             // nodes[0] = 0 (merkle.rs:273)
 }
 
 // completes a tree whose level with m nodes (m a power of two) already sits at nodes[m .. 2m)
 void merkle_finish(Context &c, void *nodes, unsigned long long m) {
     uint4 *nd = (uint4 *)nodes;
-    while (m > 1024) {
-        merkle_level_kernel<<<(unsigned)((m / 2 + 255) / 256), 256, 0, c.stream>>>(nd + 2 * m, nd + m, m / 2); c.launches++;
-        DG_CUDA(cudaGetLastError());
-        m >>= 1;
-    }
-    if (m >= 2) {
-        merkle_top_kernel<<<1, 512, 0, c.stream>>>(nd, (unsigned)m); c.launches++;
-        DG_CUDA(cudaGetLastError());
-    } else {
-        DG_CUDA(cudaMemsetAsync(nd, 0, 32, c.stream));
-    }
+    tree_levels(c, nd + 2 * m, nd, m, 1);
+    DG_CUDA(cudaMemsetAsync(nd, 0, 32, c.stream));
+}
+
+// levels of a heap-layout tree from L/2 nodes down to (and including) the level with `stop` nodes
+void merkle_levels_down_to(Context &c, const void *leaves, void *nodes, unsigned long long L, unsigned long long stop) {
+    tree_levels(c, (const uint4 *)leaves, (uint4 *)nodes, L, stop);
 }
 
 // ---- generic 64-byte hashing (tests / FRI rows given contiguously) ------------------------------------------------------

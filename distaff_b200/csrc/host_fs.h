@@ -33,6 +33,17 @@ private:
 };
 std::vector<fe> prng_vector(const uint8_t seed[32], size_t count);
 
+// Optional host-supplied randomness (dg_set_rng_callbacks): when set, prng_vector / query_positions ask the host instead of the
+// built-in restatement of rand 0.7.3 -- a Rust host passes closures over the real StdRng / Uniform, which removes the one
+// third-party semantic this library would otherwise have to reproduce from the crate's documentation.
+struct RngHooks {
+    void *user;
+    int (*draw_field)(void *user, const uint8_t seed[32], uint64_t count, uint8_t *out16);
+    int (*draw_positions)(void *user, const uint8_t seed[32], uint64_t domain_size, uint32_t extension_factor, uint32_t num_queries, uint64_t *out);
+};
+void set_rng_hooks(const RngHooks *hooks);     // nullptr: built-in generator
+bool rng_hooks_active();
+
 // ---- BLAKE3 of a short message (<= 1024 bytes) on the host -------------------------------------------------------------
 void blake3_short(const uint8_t *data, size_t len, uint8_t out[32]);
 

@@ -124,8 +124,100 @@ __global__ void scale_by_pow_kernel(const fe *__restrict__ in, fe *__restrict__ 
     out[i] = fe_mul(v, pw(t, i + offset));
 }
 
-// out[i] = sum_{j>i} (in[j] - [j==0] sub0) b^(j-i-1);   `scratch` holds len elements.  in may equal out.
+// Single-pass form (decoupled look-back, "chained scan"): one kernel reads every coefficient once and writes every quotient once.
+// Blocks take tickets in launch order and work from the top of the vector downwards; a block publishes the sum of its scaled
+// coefficients, then its first warp walks the descriptors of the blocks above it (32 at a time) until it meets one whose inclusive
+// suffix is known.  Replaces scale + block sums + recursive scan + apply + scale (7-9 launches, ~9 passes over the vector).
+struct __align__(16) ScanDesc { fe agg; fe incl; int status; int pad[3]; };     // status: 0 nothing, 1 aggregate published, 2 inclusive suffix published
+
+__device__ __forceinline__ fe ld_cg_fe(const fe *p) {
+    uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+    fe r; r.lo = ((unsigned long long)v.y << 32) | v.x; r.hi = ((unsigned long long)v.w << 32) | v.z;
+    return r;
+}
+__device__ __forceinline__ void st_cg_fe(fe *p, fe v) {
+    __stcg(reinterpret_cast<uint4 *>(p), make_uint4((unsigned)v.lo, (unsigned)(v.lo >> 32), (unsigned)v.hi, (unsigned)(v.hi >> 32)));
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) syn_div_chained_kernel(const fe *__restrict__ in, fe *__restrict__ out, unsigned long long len, PowRef bp,
+                                                                       PowRef binvp, fe sub0, ScanDesc *desc, unsigned *ticket, unsigned nblocks) {
+    __shared__ fe s_warp[SCAN_THREADS / 32];
+    __shared__ fe s_carry;
+    __shared__ unsigned s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned blk = nblocks - 1u - s_ticket;
+    const unsigned long long base = (unsigned long long)blk * SCAN_BLOCK + (unsigned long long)threadIdx.x * SCAN_PER_THREAD;
+    fe x[SCAN_PER_THREAD];
+    fe v = fe_make(0, 0);
+#pragma unroll
+    for (int u = 0; u < SCAN_PER_THREAD; u++) {
+        const unsigned long long i = base + u;
+        x[u] = fe_make(0, 0);
+        if (i < len) {
+            fe a = in[i];
+            if (i == 0) a = fe_sub(a, sub0);
+            x[u] = fe_mul(a, pw(bp, i));
+        }
+        v = fe_add(v, x[u]);
+    }
+    fe total;
+    const fe incl = block_suffix_inclusive(v, s_warp, &total);
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        ScanDesc *me = desc + blk;
+        fe carry = fe_make(0, 0);
+        if (blk == nblocks - 1u) {
+            if (lane == 0) { st_cg_fe(&me->incl, total); __threadfence(); *(volatile int *)&me->status = 2; }
+        } else {
+            if (lane == 0) { st_cg_fe(&me->agg, total); __threadfence(); *(volatile int *)&me->status = 1; }
+            for (unsigned first = blk + 1u;; first += 32u) {
+                const unsigned b2 = first + lane;
+                int st = 2;
+                fe val = fe_make(0, 0);
+                if (b2 < nblocks) {
+                    const ScanDesc *d = desc + b2;
+                    do { st = *(const volatile int *)&d->status; } while (st == 0);
+                    __threadfence();
+                    val = ld_cg_fe(st == 2 ? &d->incl : &d->agg);
+                }
+                const unsigned done = __ballot_sync(0xffffffffu, st == 2);
+                const unsigned upto = done ? (unsigned)(__ffs((int)done) - 1) : 31u;         // first lane with a complete suffix
+                if (lane > upto) val = fe_make(0, 0);
+#pragma unroll
+                for (int dd = 16; dd >= 1; dd >>= 1) val = fe_add(val, shfl_down_fe(val, dd));
+                val.lo = __shfl_sync(0xffffffffu, val.lo, 0); val.hi = __shfl_sync(0xffffffffu, val.hi, 0);
+                carry = fe_add(carry, val);
+                if (done) break;
+            }
+            if (lane == 0) { st_cg_fe(&me->incl, fe_add(total, carry)); __threadfence(); *(volatile int *)&me->status = 2; }
+        }
+        if (lane == 0) s_carry = carry;
+    }
+    __syncthreads();
+    fe run = fe_add(fe_sub(incl, v), s_carry);               // everything strictly above this thread's elements
+#pragma unroll
+    for (int u = SCAN_PER_THREAD - 1; u >= 0; u--) {
+        const unsigned long long i = base + u;
+        if (i < len) out[i] = fe_mul(run, pw(binvp, i + 1));
+        run = fe_add(run, x[u]);
+    }
+}
+
+// out[i] = sum_{j>i} (in[j] - [j==0] sub0) b^(j-i-1);   `scratch` holds len elements (used by the multi-pass form only).  in may equal out.
 void syn_div(Context &c, const fe *in, fe *out, fe *scratch, unsigned long long len, const PowRef &b_pows, const PowRef &binv_pows, fe sub0) {
+    static int chained = -1;
+    if (chained < 0) { const char *e = getenv("DG_SCAN_CHAINED"); chained = e ? atoi(e) : 1; }
+    if (chained) {
+        const unsigned long long nblk = (len + SCAN_BLOCK - 1) / SCAN_BLOCK;
+        DevBuf d((size_t)nblk * sizeof(ScanDesc) + 16);
+        DG_CUDA(cudaMemsetAsync(d.p, 0, d.bytes, c.stream));
+        ScanDesc *desc = d.as<ScanDesc>();
+        unsigned *ticket = reinterpret_cast<unsigned *>(desc + nblk);
+        syn_div_chained_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, c.stream>>>(in, out, len, b_pows, binv_pows, sub0, desc, ticket, (unsigned)nblk); c.launches++;
+        DG_CUDA(cudaGetLastError());
+        return;
+    }
     const unsigned blocks = (unsigned)((len + 255) / 256);
     scale_by_pow_kernel<<<blocks, 256, 0, c.stream>>>(in, scratch, b_pows, 0, len, sub0); c.launches++;
     DG_CUDA(cudaGetLastError());
@@ -265,6 +357,52 @@ __global__ void boundary_coeffs_kernel(const fe *__restrict__ polys, unsigned lo
 }
 void boundary_coeffs(Context &c, const fe *polys, unsigned long long n, int nb, const fe *coef, fe KiA, fe KiB, fe KfA, fe KfB, fe *ic, fe *fc) {
     boundary_coeffs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(polys, n, nb, coef, KiA, KiB, KfA, KfB, 6 * n + 2, ic, fc); c.launches++;
+    DG_CUDA(cudaGetLastError());
+}
+
+// Interpolation of 8n evaluations given coset by coset (the constraint kernel's layout): e[8k + c] = P(w_E^(8k + c)), E = 8n.
+// With m = m0 + n*m1:  e_c[k] = sum_m0 w_n^(k m0) * [ w_E^(c m0) * sum_m1 a[m0 + n m1] w_8^(c m1) ], so each coset is inverted by a size-n
+// inverse transform (b_c = iNTT_n(e_c), done by the caller; it shards by coset), and this kernel finishes: for every m0 it undoes the
+// factor w_E^(c m0) and runs the 8-point inverse DFT across the cosets.  Output: the 8n coefficients in natural order, exactly what
+// interpolate_fft of the natural-order evaluation vector returns (constraint_table.rs:54-63) -- no transposition, no 8n-point transform.
+// b: [8][n]; tw: powers of w_E^-1; w8i[j] = w_8^-j, j = 1..3; inv8 = 1/8.
+__global__ void coset_interp_finish_kernel(const fe *__restrict__ b, fe *__restrict__ out, unsigned long long n, TwiddleRef tw, fe w8i1, fe w8i2, fe w8i3, fe inv8) {
+    const unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m0 >= n) return;
+    fe x[8];
+    x[0] = fe_mul(b[m0], inv8);
+#pragma unroll
+    for (int c = 1; c < 8; c++) {
+        const unsigned e = (unsigned)((unsigned long long)c * m0) & (unsigned)tw.mask;
+        const fe t = fe_mul(fe_mul(tw.lo[e & ((1u << tw.lo_bits) - 1u)], tw.hi[e >> tw.lo_bits]), inv8);
+        x[c] = fe_mul(b[(unsigned long long)c * n + m0], t);
+    }
+    // decimation in frequency with w = w_8^-1: X[m1] = sum_c x_c w^(c m1)
+    fe u[4], v[4];
+    const fe wp[4] = {fe_make(1, 0), w8i1, w8i2, w8i3};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        u[c] = fe_add(x[c], x[c + 4]);
+        v[c] = fe_sub(x[c], x[c + 4]);
+        if (c) v[c] = fe_mul(v[c], wp[c]);
+    }
+    fe X[8];
+    {   // even outputs from u, odd outputs from v, 4-point transforms with w^2
+        fe p0 = fe_add(u[0], u[2]), p1 = fe_add(u[1], u[3]), q0 = fe_sub(u[0], u[2]), q1 = fe_mul(fe_sub(u[1], u[3]), w8i2);
+        X[0] = fe_add(p0, p1); X[4] = fe_sub(p0, p1); X[2] = fe_add(q0, q1); X[6] = fe_sub(q0, q1);
+        p0 = fe_add(v[0], v[2]); p1 = fe_add(v[1], v[3]); q0 = fe_sub(v[0], v[2]); q1 = fe_mul(fe_sub(v[1], v[3]), w8i2);
+        X[1] = fe_add(p0, p1); X[5] = fe_sub(p0, p1); X[3] = fe_add(q0, q1); X[7] = fe_sub(q0, q1);
+    }
+#pragma unroll
+    for (int m1 = 0; m1 < 8; m1++) out[m0 + n * (unsigned long long)m1] = X[m1];
+}
+void coset_interp_finish(Context &c, const fe *b, fe *out, int log_n) {
+    const unsigned long long n = 1ULL << log_n;
+    const fe w8i = host_inv(host_root_of_unity(3));
+    const fe w8i2 = fe_mul(w8i, w8i);
+    coset_interp_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(b, out, n, c.twiddle(log_n + 3, true), w8i, w8i2, fe_mul(w8i2, w8i),
+                                                                              host_inv(fe_make(8, 0)));
+    c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 

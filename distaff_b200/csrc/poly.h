@@ -18,6 +18,8 @@ void syn_div(Context &c, const fe *in, fe *out, fe *scratch, unsigned long long 
 void syn_div_expanded_sum(Context &c, const fe *a, fe *scratch, const fe *add0, const fe *add1, fe *out, unsigned long long n, unsigned long long len, fe e);
 void eval_polys_at(Context &c, const fe *polys, unsigned long long n, int cols, const PowRef &zt, const TwiddleRef &gt, bool two_points, fe *out);
 void boundary_coeffs(Context &c, const fe *polys, unsigned long long n, int nb, const fe *coef, fe KiA, fe KiB, fe KfA, fe KfB, fe *ic, fe *fc);
+// finishes the coset-by-coset interpolation of 8n evaluations: b = [8][n] size-n inverse transforms of the cosets -> 8n coefficients
+void coset_interp_finish(Context &c, const fe *b, fe *out, int log_n);
 void lincomb2(Context &c, const fe *polys, unsigned long long n, int w, const fe *cc1, const fe *cc2, fe *t1, fe *t2);
 void compose(Context &c, const fe *t1q, const fe *t2q, const fe *cq, fe *comp, unsigned long long n, unsigned long long len, unsigned long long inc,
              fe k1, fe k2, fe kc);
@@ -53,11 +55,14 @@ struct Layout {
 // leaves[r] = blake3(v[r], v[r+R], v[r+2R], v[r+3R]),  R = D/4   (fri/prover.rs:16-17, fri/utils.rs:16-21)
 void fri_hash_rows(Context &c, const fe *values, Layout in, Layout rows, void *leaves);
 // next[r] = f_r(alpha), f_r = cubic through (x_r t^j, v[r + jR])   (fri/prover.rs:26-32, quartic.rs:20-135)
-void fri_fold(Context &c, const fe *values, Layout in, fe *next, Layout out, fe alpha, const TwiddleRef &inv_root_table, int log_n_total,
+// alpha: device pointer (derived on the device by fri_alpha, or uploaded by the host when RNG callbacks are registered)
+void fri_fold(Context &c, const fe *values, Layout in, fe *next, Layout out, const fe *alpha, const TwiddleRef &inv_root_table, int log_n_total,
               fe tau_inv, fe inv4);
+// alpha_dev[0] = field::prng(root) (fri/prover.rs:29); root_copy_dev receives the 32 root bytes (collected for one host copy at the end)
+void fri_alpha(Context &c, const void *root_dev, fe *alpha_dev, void *root_copy_dev);
 // coset-sharded variants (a rank holds cosets [c0, c0 + 2^log_nc) of the layer as [c - c0][k]); items in ShardedTree order [k'][c - c0]
 void fri_hash_rows_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, void *items_local);
-void fri_fold_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, unsigned c0, fe *next_local, fe alpha,
+void fri_fold_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, unsigned c0, fe *next_local, const fe *alpha,
                     const TwiddleRef &inv_root_table, int log_n_total, fe tau_inv, fe inv4);
 // first level of the constraint tree straight from coset-major evaluations: nodes[L/2 + j] = H(ev[4j..4j+3]), L = N/2 leaves
 void constraint_tree_first_level(Context &c, const fe *evals, int log_n, int log_blowup, void *nodes);

@@ -25,6 +25,36 @@ struct StageClock {
     float between(int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, ev[a], ev[b]); return ms; }
 };
 
+// optional fine-grained device timeline (DG_SUBSTAGE=1): named event marks inside the nine stages, printed by rank 0 after the proof
+struct SubClock {
+    bool on;
+    cudaStream_t s;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    explicit SubClock(cudaStream_t stream) : on(getenv("DG_SUBSTAGE") != nullptr), s(stream) {}
+    void mark(const char *name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        marks.emplace_back(name, e);
+    }
+    void report(int rank) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        std::string line = "SUBSTAGE rank " + std::to_string(rank) + ":";
+        for (size_t i = 1; i < marks.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            char buf[96];
+            snprintf(buf, sizeof buf, " %s=%.3f", marks[i].first.c_str(), ms);
+            line += buf;
+        }
+        if (rank == 0) fprintf(stderr, "%s\n", line.c_str());
+        for (auto &m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
+};
+
 void d2h(Context &c, void *dst, const void *src, size_t bytes) {
     DG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
     DG_CUDA(cudaStreamSynchronize(c.stream));
@@ -232,6 +262,7 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
 
     ArenaScope arena_scope;                   // all DevBufs below come from the per-proof arena (no driver allocation inside a proof)
     StageClock clk(c.stream);
+    SubClock sub(c.stream);
     const unsigned long long launches0 = c.launches;
     Proof *proof = new Proof();
     std::unique_ptr<Proof> guard(proof);
@@ -247,6 +278,7 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
 
     // ---- 1: extend execution trace ---------------------------------------------------------------------------------------------------
     clk.mark(0);
+    sub.mark("start");
     // G > 1: the interpolation is sharded by columns (rank g interpolates columns [g cpr, (g + 1) cpr) and only needs -- and, from a
     // host trace, only uploads -- those registers), the polynomials are all-gathered, and every rank extends all columns on its cosets
     const int cpr = (w + G - 1) / G;                           // columns per rank (the last rank may own fewer, or none)
@@ -269,27 +301,32 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         const int j0 = std::min(w, g * cpr), mine = std::min(w, j0 + cpr) - j0;
         if (mine > 0) {
             if (host_cols) {
-                TraceUploader up(c, d_regs + (size_t)j0 * n, host_cols + j0, mine, n, mine);
-                up.wait_chunk(0);
+                TraceUploader up(c, d_regs + (size_t)j0 * n, host_cols + j0, mine, n, 1);      // one column per chunk: all staging workers busy
+                for (int i = 0; i < up.chunks(); i++) up.wait_chunk(i);
                 ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, mine, n, n, true);
             } else {
                 ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, mine, n, n, true);
             }
         }
+    sub.mark("1.intt");
         comm_all_gather(c, polys.as<fe>() + (size_t)g * cpr * n, polys.p, (size_t)cpr * n * 16);       // in place
+    sub.mark("1.gather_polys");
         lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
     }
 
     // ---- 2: trace Merkle tree ----------------------------------------------------------------------------------------------------------
     clk.mark(1);
+    sub.mark("1.lde");
     DevBuf t_leaves(N_loc * 32);
     hash_trace_rows(c, ext.as<fe>(), t_leaves.p, w, log_n, log_nc);          // local rows, [k][c - c0]
+    sub.mark("2.hash_rows");
     ShardedTree t_tree;
     t_tree.build(c, t_leaves.p, n, log_nc);
     memcpy(proof->trace_root, t_tree.root.data(), 32);
 
     // ---- 3: evaluate constraints --------------------------------------------------------------------------------------------------------
     clk.mark(2);
+    sub.mark("2.tree");
     fe last_row[3];     // op_counter and program hash of the last trace step (evaluator.rs:73-74)
     if (host_cols) {
         for (int j = 0; j < 3; j++) memcpy(&last_row[j], host_cols[j] + (n - 1) * 16, 16);
@@ -342,27 +379,33 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         static const int GROUP_DEG[6] = {2, 3, 4, 6, 7, 8};
         for (int gi = 0; gi < 6; gi++) P.inc[gi] = (8 * n - 1) - (n - 1) * GROUP_DEG[gi];
         P.violation = d_violation.as<unsigned>();
+    sub.mark("3.setup");
         launch_constraint_eval(c, P);
+    sub.mark("3.eval");
         comm_all_reduce_max_u32(c, d_violation.as<unsigned>(), 1);
         unsigned violation = 0;
         d2h(c, &violation, d_violation.p, 4);
         if (violation) throw Error(DG_ERR_UNSATISFIED, "transition constraints at step " + std::to_string(violation - 1) + " were not satisfied");
-        // every rank interpolates the transition combination: gather the coset slabs, then go to natural step order
+        // interpolation of the transition combination (constraint_table.rs:54-63), coset by coset: size-n inverse transforms of the own
+        // cosets (sharded), all-gather, then the 8-point inverse DFT across cosets (poly.cu: coset_interp_finish) -> the 8n coefficients
+        // in natural order; no transposition and no replicated 8n-point transform
+    sub.mark("3.violation_sync");
+        ntt_batch(c, evals_loc.as<fe>(), evals_loc.as<fe>(), log_n, num_c8, n, n, true);
         comm_all_gather(c, evals_loc.as<fe>(), gathered.as<fe>(), E_loc * 16);
-        transpose_cosets(c, gathered.as<fe>(), evals.as<fe>() + 2 * E, log_n, 3, 1);
+    sub.mark("3.intt+gather");
+        coset_interp_finish(c, gathered.as<fe>(), evals.as<fe>() + 2 * E, log_n);
         // boundary constraints (evaluator.rs:181-326), directly as the 8n coefficients the reference obtains by interpolation
         boundary_coeffs(c, polys.as<fe>(), n, (int)nb, base + 2 * T, cc.KiA, cc.KiB, cc.KfA, cc.KfB, evals.as<fe>(), evals.as<fe>() + E);
     }
-    debug_dump(c, "t_evals", evals.as<fe>() + 2 * E, E * 16);
+    debug_dump(c, "t_coeffs", evals.as<fe>() + 2 * E, E * 16);
 
     // ---- 4: convert constraint evaluations into a polynomial -----------------------------------------------------------------------------
     clk.mark(3);
-    const int log_E = log_n + 3;
+    sub.mark("3.finish+boundary");
     DevBuf combined(E * 16), scratch(E * 16), scratch2(E * 16);
     const fe root_n = host_root_of_unity(log_n);
     const fe x_last = host_inv(root_n);                        // w_n^(n-1)   (evaluator.rs:128-131)
     {
-        ntt_batch(c, evals.as<fe>() + 2 * E, evals.as<fe>() + 2 * E, log_E, 1, E, E, true);
         debug_dump(c, "i_coeffs", evals.as<fe>(), E * 16);
         debug_dump(c, "f_coeffs", evals.as<fe>() + E, E * 16);
         fe *ic = evals.as<fe>(), *fc = evals.as<fe>() + E, *tc = evals.as<fe>() + 2 * E;
@@ -375,15 +418,19 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
 
     // ---- 5: constraint evaluations over the LDE domain + their Merkle tree -----------------------------------------------------------------
     clk.mark(4);
+    sub.mark("4.combine");
     DevBuf c_ext(N_loc * 16), c_items((N_loc / 4) * 32);
     lde_batch(c, combined.as<fe>(), c_ext.as<fe>(), log_n, log_b, 8, 1, E, N_loc, c0, (unsigned)nc);
+    sub.mark("5.lde");
     constraint_items_local(c, c_ext.as<fe>(), log_n, log_nc, c_items.p);      // first tree level: H(4 evaluations), [k][c4 local]
+    sub.mark("5.items");
     ShardedTree c_tree;
     c_tree.build(c, c_items.p, n, log_nc - 2);
     memcpy(proof->constraint_root, c_tree.root.data(), 32);
 
     // ---- 6: DEEP composition polynomial ---------------------------------------------------------------------------------------------------------
     clk.mark(5);
+    sub.mark("5.tree");
     fs::CompositionCoefficients dc = fs::draw_composition_coefficients(proof->constraint_root, w);
     const fe z = dc.z, zg = fe_mul(z, root_n);
     std::vector<fe> state1(w), state2(w);
@@ -391,18 +438,25 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
     {
         PowTable z_t(c, z, E + 1), zi_t(c, host_inv(z), E + 1), zg_t(c, zg, n + 1), zgi_t(c, host_inv(zg), n + 1);
         TwiddleRef g_t = c.twiddle(log_n, false);
-        DevBuf d_deep((size_t)(2 * w + 2) * 16);
-        eval_polys_at(c, polys.as<fe>(), n, w, z_t.ref(), g_t, true, d_deep.as<fe>());
-        eval_polys_at(c, combined.as<fe>(), E, 1, z_t.ref(), g_t, false, d_deep.as<fe>() + 2 * w);
-        std::vector<fe> deep(2 * w + 2);
+        // trace polynomials at z and z*g: every rank evaluates its own columns (the split of stage 1), the 2 cpr values per rank are gathered
+        const int wp = cpr * G;
+        DevBuf d_deep((size_t)(2 * wp + 2) * 16);
+        {
+            const int j0 = std::min(w, g * cpr), mine = std::min(w, j0 + cpr) - j0;
+            if (mine > 0) eval_polys_at(c, polys.as<fe>() + (size_t)j0 * n, n, mine, z_t.ref(), g_t, true, d_deep.as<fe>() + 2 * j0);
+            if (G > 1) comm_all_gather(c, d_deep.as<fe>() + (size_t)2 * g * cpr, d_deep.p, (size_t)2 * cpr * 16);
+        }
+        eval_polys_at(c, combined.as<fe>(), E, 1, z_t.ref(), g_t, false, d_deep.as<fe>() + 2 * wp);
+        std::vector<fe> deep(2 * wp + 2);
         d2h(c, deep.data(), d_deep.p, deep.size() * 16);
+    sub.mark("6.deep_values");
         fe sub1 = fe_make(0, 0), sub2 = fe_make(0, 0);
         for (int i = 0; i < w; i++) {
             state1[i] = deep[2 * i]; state2[i] = deep[2 * i + 1];
             sub1 = fe_add(sub1, fe_mul(state1[i], dc.trace1[i]));
             sub2 = fe_add(sub2, fe_mul(state2[i], dc.trace2[i]));
         }
-        const fe c_at_z = deep[2 * w];
+        const fe c_at_z = deep[2 * wp];
         DevBuf d_cc((size_t)2 * w * 16), t12(2 * n * 16);
         h2d(c, d_cc.p, dc.trace1.data(), (size_t)w * 16);
         h2d(c, d_cc.as<fe>() + w, dc.trace2.data(), (size_t)w * 16);
@@ -411,6 +465,7 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         syn_div(c, t1, t1, scratch.as<fe>(), n, z_t.ref(), zi_t.ref(), sub1);                          // (T1(x) - T1(z)) / (x - z)
         syn_div(c, t2, t2, scratch.as<fe>(), n, zg_t.ref(), zgi_t.ref(), sub2);                        // (T2(x) - T2(zg)) / (x - zg)
         syn_div(c, combined.as<fe>(), scratch2.as<fe>(), scratch.as<fe>(), E, z_t.ref(), zi_t.ref(), c_at_z);   // (C(x) - C(z)) / (x - z)
+    sub.mark("6.lincomb+syndiv");
         compose(c, t1, t2, scratch2.as<fe>(), comp.as<fe>(), n, E, 6 * n + 1, dc.t1_degree, dc.t2_degree, dc.constraints);
         debug_dump(c, "composition_poly", comp.p, E * 16);
         // every rank extends its own cosets; the first FRI layers work on these slabs directly (no all-gather of the N evaluations)
@@ -419,6 +474,7 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
 
     // ---- 7: FRI layers ---------------------------------------------------------------------------------------------------------------------------
     clk.mark(6);
+    sub.mark("6.compose+lde");
     std::vector<FriLayerDev> layers;
     DevBuf fri_gathered;                                       // multi-GPU: the first replicated layer, gathered from the ranks' slabs
     {
@@ -428,6 +484,24 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         const fe *cur = comp_ext.as<fe>();
         Layout lay{log_N, log_b};
         bool local = G > 1;                                    // `cur` is this rank's coset slab of the layer
+        // layer roots and folding points stay on the device (special_x = prng(root) is derived by fri_alpha): the host sees the roots
+        // in one copy after the last layer.  With host RNG callbacks registered each layer asks the host instead.
+        const int MAX_LAYERS = 20;
+        DevBuf d_alpha(MAX_LAYERS * 16), d_roots(MAX_LAYERS * 32);
+        const bool host_rng = fs::rng_hooks_active();
+        auto folding_point = [&](const void *root_dev, size_t layer) -> const fe * {
+            DG_REQUIRE(layer < (size_t)MAX_LAYERS, "too many FRI layers");
+            fe *a_dev = d_alpha.as<fe>() + layer;
+            uint8_t *r_dev = (uint8_t *)d_roots.p + 32 * layer;
+            if (!host_rng) { fri_alpha(c, root_dev, a_dev, r_dev); return a_dev; }
+            Digest r;
+            d2h(c, r.data(), root_dev, 32);
+            const fe alpha = fs::prng_vector(r.data(), 1)[0];          // field::prng(seed) = first draw of the generator (field.rs:264-269)
+            DG_CUDA(cudaMemcpyAsync(r_dev, root_dev, 32, cudaMemcpyDeviceToDevice, c.stream));
+            DG_CUDA(cudaMemcpyAsync(a_dev, &alpha, 16, cudaMemcpyHostToDevice, c.stream));
+            DG_CUDA(cudaStreamSynchronize(c.stream));
+            return a_dev;
+        };
         for (;;) {
             const int log_r = lay.log_d - 2;
             const uint64_t R = 1ULL << log_r;
@@ -438,16 +512,15 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
                 local = false;
             }
             layers.emplace_back();
+            const size_t li = layers.size() - 1;
             FriLayerDev &L = layers.back();
             L.vals = cur; L.layout = lay; L.sharded = local;
             if (local) {
                 // rows r = b k' + c of the own cosets: hashes in ShardedTree order, n' = R / b subtrees of nc leaves per rank
                 L.leaves.alloc((R >> log_g) * 32);
                 fri_hash_rows_local(c, cur, lay.log_d, log_b, log_nc, L.leaves.p);
-                L.tree.build(c, L.leaves.p, R >> log_b, log_nc);
-                L.root = L.tree.root;
-                fs::Rng rng(L.root.data());
-                const fe alpha = rng.field();
+                L.tree.build(c, L.leaves.p, R >> log_b, log_nc, false);
+                const fe *alpha = folding_point(L.tree.root_dev(), li);
                 L.folded.alloc((R >> log_g) * 16);
                 fri_fold_local(c, cur, lay.log_d, log_b, log_nc, c0, L.folded.as<fe>(), alpha, inv_root, log_N, tau_inv, inv4);
                 cur = L.folded.as<fe>();
@@ -458,19 +531,25 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
             L.leaves.alloc(R * 32); L.nodes.alloc(R * 32);
             fri_hash_rows(c, cur, lay, rows, L.leaves.p);
             merkle_build(c, L.leaves.p, L.nodes.p, R);
-            d2h(c, L.root.data(), (const uint8_t *)L.nodes.p + 32, 32);
-            if (R * 4 <= 256) break;                              // MAX_REMAINDER_LENGTH (fri/mod.rs:13)
-            fs::Rng rng(L.root.data());
-            const fe alpha = rng.field();                          // special_x = prng(root)  (fri/prover.rs:29)
+            if (R * 4 <= 256) {                                    // MAX_REMAINDER_LENGTH (fri/mod.rs:13): the remainder's root only
+                DG_REQUIRE(li < (size_t)MAX_LAYERS, "too many FRI layers");
+                DG_CUDA(cudaMemcpyAsync((uint8_t *)d_roots.p + 32 * li, (const uint8_t *)L.nodes.p + 32, 32, cudaMemcpyDeviceToDevice, c.stream));
+                break;
+            }
+            const fe *alpha = folding_point((const uint8_t *)L.nodes.p + 32, li);     // special_x = prng(root)  (fri/prover.rs:29)
             L.folded.alloc(R * 16);                                // values of the next layer, owned by this one
             fri_fold(c, cur, lay, L.folded.as<fe>(), rows, alpha, inv_root, log_N, tau_inv, inv4);
             cur = L.folded.as<fe>();
             lay = rows;
         }
+        std::vector<uint8_t> roots(32 * layers.size());
+        d2h(c, roots.data(), d_roots.p, roots.size());
+        for (size_t i = 0; i < layers.size(); i++) memcpy(layers[i].root.data(), roots.data() + 32 * i, 32);
     }
 
     // ---- 8: query positions ------------------------------------------------------------------------------------------------------------------------
     clk.mark(7);
+    sub.mark("7.fri");
     std::vector<uint64_t> positions;
     {
         std::vector<uint8_t> roots;
@@ -488,6 +567,7 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
 
     // ---- 9: build proof object -------------------------------------------------------------------------------------------------------------------------
     clk.mark(8);
+    sub.mark("8.pow");
     fs::ByteWriter out;
     {
         // Plan every opening on the host, fetch all opened values / digests in one batched pass (FetchBatch), then serialise.
@@ -616,6 +696,8 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         out.u8((uint8_t)log_b); out.u8((uint8_t)opt.num_queries); out.u8((uint8_t)opt.grinding_factor); out.u8(0);
     }
     clk.mark(9);
+    sub.mark("9.openings");
+    sub.report(c.rank);
     DG_CUDA(cudaStreamSynchronize(c.stream));
     proof->bytes = std::move(out.b);
     if (stats) {

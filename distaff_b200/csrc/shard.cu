@@ -45,15 +45,10 @@ __global__ void __launch_bounds__(256) hash_pairs_kernel(const uint4 *__restrict
     out[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
 
-// levels of a heap-layout tree from L/2 nodes down to (and including) the level with `stop` nodes
+// levels of a heap-layout tree from L/2 nodes down to (and including) the level with `stop` nodes (hash.cu: fused levels)
+void merkle_levels_down_to(Context &c, const void *leaves, void *nodes, unsigned long long L, unsigned long long stop);
 void merkle_build_partial(Context &c, const void *leaves, void *nodes, unsigned long long L, unsigned long long stop) {
-    uint4 *nd = (uint4 *)nodes;
-    const uint4 *in = (const uint4 *)leaves;
-    for (unsigned long long m = L / 2; m >= stop && m >= 1; m >>= 1) {
-        hash_pairs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(in, nd + 2 * m, m); c.launches++;
-        DG_CUDA(cudaGetLastError());
-        in = nd + 2 * m;
-    }
+    merkle_levels_down_to(c, leaves, nodes, L, stop);
 }
 
 // upper[(n << log_g) + (k << log_g) + g] = gathered[g][k]
@@ -112,26 +107,37 @@ void constraint_items_local(Context &c, const fe *evals_local, int log_n, int lo
 }
 
 // ---- sharded tree -------------------------------------------------------------------------------------------------------------------
-void ShardedTree::build(Context &c, const void *items_local_dev, uint64_t n, int log_blk) {
+void ShardedTree::build(Context &c, const void *items_local_dev, uint64_t n, int log_blk, bool fetch_root) {
     int log_g = 0;
     while ((1 << log_g) < c.world) log_g++;
     geom.n = n; geom.log_blk = log_blk; geom.log_g = log_g;
     items_local = items_local_dev;
     const uint64_t local_items = n << log_blk;
-    const void *roots = items_local_dev;
-    if (log_blk > 0) {
+    if (c.world == 1) {
+        // one rank: the local heap is the whole tree (its top 2n nodes double as the "replicated upper heap": same heap indices)
+        DG_REQUIRE(local_items >= 2, "tree needs at least 2 items");
         local_nodes.alloc(local_items * 32);
-        merkle_build_partial(c, items_local_dev, local_nodes.p, local_items, n);
-        roots = (const uint8_t *)local_nodes.p + n * 32;           // heap level with n nodes
+        merkle_build(c, items_local_dev, local_nodes.p, local_items);
+        upper_p = local_nodes.p;
+    } else {
+        const void *roots = items_local_dev;
+        if (log_blk > 0) {
+            local_nodes.alloc(local_items * 32);
+            merkle_build_partial(c, items_local_dev, local_nodes.p, local_items, n);
+            roots = (const uint8_t *)local_nodes.p + n * 32;           // heap level with n nodes
+        }
+        const uint64_t upper_level = n << log_g;
+        upper.alloc(2 * upper_level * 32);
+        DevBuf gathered(upper_level * 32);
+        comm_all_gather(c, roots, gathered.p, n * 32);
+        interleave_roots(c, gathered.p, upper.p, n, log_g);
+        merkle_finish(c, upper.p, upper_level);
+        upper_p = upper.p;
     }
-    const uint64_t upper_level = n << log_g;
-    upper.alloc(2 * upper_level * 32);
-    DevBuf gathered(upper_level * 32);
-    comm_all_gather(c, roots, gathered.p, n * 32);
-    interleave_roots(c, gathered.p, upper.p, n, log_g);
-    merkle_finish(c, upper.p, upper_level);
-    DG_CUDA(cudaMemcpyAsync(root.data(), (const uint8_t *)upper.p + 32, 32, cudaMemcpyDeviceToHost, c.stream));
-    DG_CUDA(cudaStreamSynchronize(c.stream));
+    if (fetch_root) {
+        DG_CUDA(cudaMemcpyAsync(root.data(), (const uint8_t *)upper_p + 32, 32, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaStreamSynchronize(c.stream));
+    }
 }
 
 std::vector<uint8_t> exchange_owned(Context &c, const void *d_local, size_t count, size_t item_bytes, const std::vector<int> &owners) {
@@ -210,7 +216,7 @@ std::vector<Digest> ShardedTree::fetch_nodes(Context &c, const std::vector<uint6
     if (!up_idx.empty()) {   // replicated: purely local
         DevBuf d_idx(up_idx.size() * 8), d_out(up_idx.size() * 32);
         DG_CUDA(cudaMemcpyAsync(d_idx.p, up_idx.data(), up_idx.size() * 8, cudaMemcpyHostToDevice, c.stream));
-        gather32(c, upper.p, d_idx.as<unsigned long long>(), (int)up_idx.size(), d_out.p);
+        gather32(c, upper_p, d_idx.as<unsigned long long>(), (int)up_idx.size(), d_out.p);
         std::vector<Digest> got(up_idx.size());
         DG_CUDA(cudaMemcpyAsync(got.data(), d_out.p, got.size() * 32, cudaMemcpyDeviceToHost, c.stream));
         DG_CUDA(cudaStreamSynchronize(c.stream));

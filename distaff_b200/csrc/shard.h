@@ -61,9 +61,12 @@ struct ShardedTree {
     const void *items_local = nullptr;   // n * blk digests, [k][j]
     DevBuf local_nodes;                  // heap over the local items (valid for levels with >= n nodes)
     DevBuf upper;                        // replicated heap: 2 * n * G digests, level with n*G nodes at [nG, 2nG)
+    const void *upper_p = nullptr;       // the upper heap (one rank: the local heap itself)
     Digest root;
 
-    void build(Context &c, const void *items_local_dev, uint64_t n, int log_blk);
+    // fetch_root = false leaves the root on the device (upper_p + 32): no host synchronisation
+    void build(Context &c, const void *items_local_dev, uint64_t n, int log_blk, bool fetch_root = true);
+    const void *root_dev() const { return (const uint8_t *)upper_p + 32; }
     // collective fetches (every rank passes the same lists); results in request order
     std::vector<Digest> fetch_nodes(Context &c, const std::vector<uint64_t> &heap_indices) const;
     std::vector<Digest> fetch_items(Context &c, const std::vector<uint64_t> &item_indices) const;
@@ -71,7 +74,7 @@ struct ShardedTree {
     FetchRef item_ref(uint64_t item_index) const { ShardLocation l = geom.item(item_index); return FetchRef{items_local, l.index, l.owner}; }
     FetchRef node_ref(uint64_t heap_index) const {
         ShardLocation l = geom.node(heap_index);
-        if (l.upper) return FetchRef{upper.p, l.index, -1};
+        if (l.upper) return FetchRef{upper_p, l.index, -1};
         return FetchRef{local_nodes.p, l.index, l.owner};
     }
 };
@@ -81,6 +84,8 @@ struct ShardedTree {
 std::vector<uint8_t> exchange_owned(Context &c, const void *d_local, size_t count, size_t item_bytes, const std::vector<int> &owners);
 
 void merkle_build_partial(Context &c, const void *leaves, void *nodes, unsigned long long L, unsigned long long stop);
+void merkle_build(Context &c, const void *leaves, void *nodes, unsigned long long L);
+void merkle_finish(Context &c, void *nodes, unsigned long long m);
 void interleave_roots(Context &c, const void *gathered, void *upper, unsigned long long n, int log_g);
 void transpose_cosets(Context &c, const fe *in, fe *out, int log_n, int log_c, int batch);   // [batch][2^log_c][n] -> [batch][n][2^log_c]
 void constraint_items_local(Context &c, const fe *evals_local, int log_n, int log_nc, void *items);   // [k][c4_local] digests

@@ -66,6 +66,24 @@ int dg_prove_device(const void *d_registers, uint32_t width, uint64_t length, ui
                     const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs,
                     const dg_options_t *options, dg_proof_t **proof_out, dg_prove_stats_t *stats);
 
+/* Optional: randomness supplied by the host.  The prover derives all of its Fiat-Shamir challenges from two reference functions,
+ *   field::prng_vector(seed, n)                            (math/field.rs:264-275: StdRng::from_seed + Uniform(0..M))
+ *   utils::compute_query_positions(seed, domain, options)  (stark/utils/mod.rs:25-44: StdRng + Uniform(0..domain), rejections)
+ * both built on rand 0.7.3, which is not part of the reference tree.  By default the library uses its own restatement of that
+ * generator (ChaCha20, rand's widening-multiply rejection sampling); a Rust host can instead register callbacks that call the real
+ * functions, so that no third-party semantics are reproduced on this side of the boundary.  Callbacks return 0 on success; they are
+ * called on the thread that calls dg_prove, 20-30 times per proof (once per commitment).  draw_field writes `count` canonical field
+ * elements (16 LE bytes each); draw_positions writes exactly num_queries distinct positions < domain_size, none a multiple of
+ * extension_factor (anything else is rejected with DG_ERR_INVALID; a non-zero return maps to DG_ERR_EXHAUSTED like the reference's panic).
+ * Passing NULL restores the built-in generator.  Process-wide; not to be changed while a proof is running. */
+typedef struct {
+    void *user;
+    int (*draw_field)(void *user, const uint8_t seed[32], uint64_t count, uint8_t *out16);
+    int (*draw_positions)(void *user, const uint8_t seed[32], uint64_t domain_size, uint32_t extension_factor, uint32_t num_queries,
+                          uint64_t *out_positions);
+} dg_rng_callbacks_t;
+int dg_set_rng_callbacks(const dg_rng_callbacks_t *callbacks);
+
 /* bincode 1.3.1 encoding of StarkProof (proof.rs:10-37), what main.rs:45 serialises */
 int dg_proof_serialized_len(const dg_proof_t *proof, size_t *len);
 int dg_proof_serialize(const dg_proof_t *proof, uint8_t *buf, size_t cap);

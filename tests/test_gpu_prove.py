@@ -105,3 +105,43 @@ def test_argument_validation(dg, small):
         dg.prove(short)                          # trace shorter than MIN_TRACE_LENGTH
     with pytest.raises(AssertionError):
         dg.ProofOptions(8, 50, 20)               # options.rs:36
+
+
+def test_host_rng_callbacks_give_the_same_proof(dg, po, small):
+    """dg_set_rng_callbacks: all Fiat-Shamir draws supplied by the host -- here by the oracle's restatement of
+    field::prng_vector (field.rs:264-275) and compute_query_positions (stark/utils/mod.rs:25-44) through C function pointers -- must give
+    the byte-identical proof, and the callbacks must really be on the path (call counts, failure propagation)."""
+    from distaff_b200 import backend, felt
+    calls = {"field": 0, "positions": 0}
+
+    def draw_field(seed, count):
+        calls["field"] += 1
+        return felt.from_ints(po.prng_vector(seed, count)).tobytes()
+
+    def draw_positions(seed, domain, ext, nq):
+        calls["positions"] += 1
+        return po.query_positions(seed, domain, ext, nq)
+
+    try:
+        for name in ("fib13", "collatz3", "hash"):
+            tr = small[name]
+            backend.set_rng_callbacks()
+            want = dg.prove(tr).bytes
+            backend.set_rng_callbacks(draw_field, draw_positions)
+            before = dict(calls)
+            got = dg.prove(tr).bytes
+            assert got == want, name
+            assert calls["positions"] == before["positions"] + 1
+            assert calls["field"] >= before["field"] + 3          # constraint coefficients, composition coefficients, >= 1 FRI layer
+        # a failing position callback surfaces as the reference's "needed more query positions" condition (DG_ERR_EXHAUSTED)
+        backend.set_rng_callbacks(draw_field, lambda *a: (_ for _ in ()).throw(RuntimeError("no")))
+        with pytest.raises(backend.DgError) as e:
+            dg.prove(small["fib13"])
+        assert e.value.code == -4
+        # positions that violate compute_query_positions' invariants are rejected, not proven
+        backend.set_rng_callbacks(draw_field, lambda seed, domain, ext, nq: [ext * (i + 1) for i in range(nq)])
+        with pytest.raises(backend.DgError):
+            dg.prove(small["fib13"])
+    finally:
+        backend.set_rng_callbacks()
+    assert dg.prove(small["fib13"]).bytes == dg.prove(small["fib13"]).bytes
