@@ -365,7 +365,7 @@ int dg_host_shard_locate(uint64_t n, int log_blk, int log_g, int is_node, uint64
     return guarded([&] {
         ShardGeom geo; geo.n = n; geo.log_blk = log_blk; geo.log_g = log_g;
         ShardLocation l = is_node ? geo.node(index) : geo.item(index);
-        out[0] = l.owner; out[1] = l.upper ? 1 : 0; out[2] = (int64_t)l.index;
+        out[0] = l.owner; out[1] = l.kind; out[2] = (int64_t)l.index;
     });
 }
 

@@ -16,6 +16,8 @@ typedef int (*fn_CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
 typedef int (*fn_AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
 typedef int (*fn_AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
 typedef int (*fn_CommDestroy)(ncclComm_t);
+typedef int (*fn_SendRecv)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*fn_Group)(void);
 typedef const char *(*fn_GetErrorString)(int);
 
 struct Nccl {
@@ -25,6 +27,8 @@ struct Nccl {
     fn_AllGather AllGather = nullptr;
     fn_AllReduce AllReduce = nullptr;
     fn_CommDestroy CommDestroy = nullptr;
+    fn_SendRecv Send = nullptr, Recv = nullptr;
+    fn_Group GroupStart = nullptr, GroupEnd = nullptr;
     fn_GetErrorString GetErrorString = nullptr;
     ncclComm_t comm = nullptr;
 } g_nccl;
@@ -45,6 +49,10 @@ void load_nccl() {
     g_nccl.AllGather = (fn_AllGather)sym("ncclAllGather");
     g_nccl.AllReduce = (fn_AllReduce)sym("ncclAllReduce");
     g_nccl.CommDestroy = (fn_CommDestroy)sym("ncclCommDestroy");
+    g_nccl.Send = (fn_SendRecv)sym("ncclSend");
+    g_nccl.Recv = (fn_SendRecv)sym("ncclRecv");
+    g_nccl.GroupStart = (fn_Group)sym("ncclGroupStart");
+    g_nccl.GroupEnd = (fn_Group)sym("ncclGroupEnd");
     g_nccl.GetErrorString = (fn_GetErrorString)sym("ncclGetErrorString");
 }
 void nccl_check(int rc, const char *what) {
@@ -85,6 +93,20 @@ void comm_all_gather(Context &c, const void *send, void *recv, size_t bytes) {
         return;
     }
     nccl_check(g_nccl.AllGather(send, recv, bytes, /*ncclUint8*/ 1, g_nccl.comm, c.stream), "ncclAllGather");
+}
+
+// recv[g] (bytes each) = the chunk rank g sent to this rank; send[h] = the chunk for rank h.  One grouped send/recv per peer.
+void comm_all_to_all(Context &c, const void *send, void *recv, size_t bytes) {
+    if (c.world == 1) {
+        if (send != recv) DG_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, c.stream));
+        return;
+    }
+    nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
+    for (int p = 0; p < c.world; p++) {
+        nccl_check(g_nccl.Send((const uint8_t *)send + (size_t)p * bytes, bytes, /*ncclUint8*/ 1, p, g_nccl.comm, c.stream), "ncclSend");
+        nccl_check(g_nccl.Recv((uint8_t *)recv + (size_t)p * bytes, bytes, /*ncclUint8*/ 1, p, g_nccl.comm, c.stream), "ncclRecv");
+    }
+    nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
 }
 
 // in-place max over ranks of `count` uint32 values

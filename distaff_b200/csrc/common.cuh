@@ -166,6 +166,7 @@ void comm_unique_id(uint8_t out[128]);
 void comm_init(Context &c, int rank, int world, const uint8_t id_bytes[128]);
 void comm_finalize(Context &c);
 void comm_all_gather(Context &c, const void *send, void *recv, size_t bytes_per_rank);
+void comm_all_to_all(Context &c, const void *send, void *recv, size_t bytes_per_peer);
 void comm_all_reduce_max_u32(Context &c, unsigned *buf, size_t count);
 
 }  // namespace dg

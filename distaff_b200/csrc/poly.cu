@@ -423,40 +423,4 @@ void compose(Context &c, const fe *t1q, const fe *t2q, const fe *cq, fe *comp, u
     DG_CUDA(cudaGetLastError());
 }
 
-// ---- gathers for the query openings -----------------------------------------------------------------------------------------------------------
-// out[q*w + j] = ext[j * col_stride + phys_q]   (phys_q = position inside the rank's coset-major slab, computed on the host)
-__global__ void gather_rows_kernel(const fe *__restrict__ ext, int w, unsigned long long col_stride, const unsigned long long *__restrict__ phys,
-                                   int nq, fe *__restrict__ out) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nq * w) return;
-    int q = t / w, j = t % w;
-    out[t] = ext[(unsigned long long)j * col_stride + phys[q]];
-}
-void gather_rows(Context &c, const fe *ext, int w, unsigned long long col_stride, const unsigned long long *d_phys, int nq, fe *d_out) {
-    gather_rows_kernel<<<(nq * w + 127) / 128, 128, 0, c.stream>>>(ext, w, col_stride, d_phys, nq, d_out); c.launches++;
-    DG_CUDA(cudaGetLastError());
-}
-// out[t] = src[idx[t]] for 32-byte items
-__global__ void gather32_kernel(const uint4 *__restrict__ src, const unsigned long long *__restrict__ idx, int count, uint4 *__restrict__ out) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    out[2 * t] = src[2 * idx[t]];
-    out[2 * t + 1] = src[2 * idx[t] + 1];
-}
-void gather32(Context &c, const void *src, const unsigned long long *d_idx, int count, void *d_out) {
-    if (count == 0) return;
-    gather32_kernel<<<(count + 127) / 128, 128, 0, c.stream>>>((const uint4 *)src, d_idx, count, (uint4 *)d_out); c.launches++;
-    DG_CUDA(cudaGetLastError());
-}
-// out[t] = src[idx[t]] for 16-byte items
-__global__ void gather16_kernel(const fe *__restrict__ src, const unsigned long long *__restrict__ idx, int count, fe *__restrict__ out) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < count) out[t] = src[idx[t]];
-}
-void gather16(Context &c, const fe *src, const unsigned long long *d_idx, int count, fe *d_out) {
-    if (count == 0) return;
-    gather16_kernel<<<(count + 127) / 128, 128, 0, c.stream>>>(src, d_idx, count, d_out); c.launches++;
-    DG_CUDA(cudaGetLastError());
-}
-
 }  // namespace dg

@@ -23,9 +23,6 @@ void coset_interp_finish(Context &c, const fe *b, fe *out, int log_n);
 void lincomb2(Context &c, const fe *polys, unsigned long long n, int w, const fe *cc1, const fe *cc2, fe *t1, fe *t2);
 void compose(Context &c, const fe *t1q, const fe *t2q, const fe *cq, fe *comp, unsigned long long n, unsigned long long len, unsigned long long inc,
              fe k1, fe k2, fe kc);
-void gather_rows(Context &c, const fe *ext, int w, unsigned long long col_stride, const unsigned long long *d_phys, int nq, fe *d_out);
-void gather32(Context &c, const void *src, const unsigned long long *d_idx, int count, void *d_out);
-void gather16(Context &c, const fe *src, const unsigned long long *d_idx, int count, fe *d_out);
 
 // ---- hashing (hash.cu) ----
 void hash_trace_rows(Context &c, const fe *ext, void *leaves, int w, int log_n, int log_blowup);

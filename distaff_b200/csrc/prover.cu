@@ -87,40 +87,6 @@ void debug_dump_host(const char *name, const void *host, size_t bytes) {
 }
 
 
-// fetches 32-byte items src[idx[i]] to the host
-std::vector<Digest> fetch32(Context &c, const void *src, const std::vector<uint64_t> &idx) {
-    std::vector<Digest> out(idx.size());
-    if (idx.empty()) return out;
-    DevBuf d_idx(idx.size() * 8), d_out(idx.size() * 32);
-    h2d(c, d_idx.p, idx.data(), idx.size() * 8);
-    gather32(c, src, d_idx.as<unsigned long long>(), (int)idx.size(), d_out.p);
-    d2h(c, out.data(), d_out.p, idx.size() * 32);
-    return out;
-}
-std::vector<fe> fetch16(Context &c, const fe *src, const std::vector<uint64_t> &idx) {
-    std::vector<fe> out(idx.size());
-    if (idx.empty()) return out;
-    DevBuf d_idx(idx.size() * 8), d_out(idx.size() * 16);
-    h2d(c, d_idx.p, idx.data(), idx.size() * 8);
-    gather16(c, src, d_idx.as<unsigned long long>(), (int)idx.size(), d_out.as<fe>());
-    d2h(c, out.data(), d_out.p, idx.size() * 16);
-    return out;
-}
-
-// materialises the node lists of a batch proof; `leaf_fetch` maps leaf indices and `node_fetch` heap indices to 32-byte values
-template <typename LeafFetch, typename NodeFetch>
-std::vector<std::vector<Digest>> resolve_plan(const fs::BatchPlan &plan, LeafFetch leaf_fetch, NodeFetch node_fetch) {
-    std::vector<uint64_t> leaf_idx, node_idx;
-    for (auto &slot : plan.nodes)
-        for (auto &r : slot) (r.leaf ? leaf_idx : node_idx).push_back(r.index);
-    std::vector<Digest> leaves = leaf_fetch(leaf_idx), nodes = node_fetch(node_idx);
-    std::vector<std::vector<Digest>> out(plan.nodes.size());
-    size_t li = 0, ni = 0;
-    for (size_t s = 0; s < plan.nodes.size(); s++)
-        for (auto &r : plan.nodes[s]) out[s].push_back(r.leaf ? leaves[li++] : nodes[ni++]);
-    return out;
-}
-
 void write_digest_vec(fs::ByteWriter &w, const std::vector<Digest> &v) {
     w.u64(v.size());
     for (auto &d : v) w.raw(d.data(), 32);

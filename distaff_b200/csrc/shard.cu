@@ -10,22 +10,27 @@ ShardLocation ShardGeom::item(uint64_t i) const {
     const uint64_t k = i / per_k, within = i % per_k;
     ShardLocation r;
     r.owner = (int)(within >> log_blk);
-    r.upper = false;
+    r.kind = SHARD_LOCAL;
     r.index = (k << log_blk) + (within & (blk - 1));
     return r;
 }
 ShardLocation ShardGeom::node(uint64_t h) const {
-    const uint64_t upper_nodes = n << log_g;              // the replicated tree holds heap indices [1, 2 * n * G)
+    const uint64_t G = 1ULL << log_g;
+    const int lvl = 63 - __builtin_clzll(h);
+    const uint64_t S = 1ULL << lvl, o = h - S;              // level size, position inside the level
     ShardLocation r;
-    if (h < 2 * upper_nodes) { r.owner = -1; r.upper = true; r.index = h; return r; }
-    int lvl = 63 - __builtin_clzll(h);
-    const uint64_t S = 1ULL << lvl, o = h - S;
+    if (S <= G) { r.owner = -1; r.kind = SHARD_TOP; r.index = h; return r; }                   // replicated top heap (levels 1 .. G)
+    if (S <= n * G) {                                       // mid: every rank holds S / G consecutive nodes of this level
+        const uint64_t per = S / G;
+        r.owner = (int)(o / per); r.kind = SHARD_MID; r.index = per + (o % per);
+        return r;
+    }
     const uint64_t span = items() / S;                    // level-0 items below this node (< blk)
     const uint64_t i0 = o * span;
     ShardLocation it = item(i0);
     const uint64_t local_level = (n << log_blk) / span;   // size of the local level with the same span
     r.owner = it.owner;
-    r.upper = false;
+    r.kind = SHARD_LOCAL;
     r.index = local_level + it.index / span;
     return r;
 }
@@ -112,48 +117,37 @@ void ShardedTree::build(Context &c, const void *items_local_dev, uint64_t n, int
     while ((1 << log_g) < c.world) log_g++;
     geom.n = n; geom.log_blk = log_blk; geom.log_g = log_g;
     items_local = items_local_dev;
-    const uint64_t local_items = n << log_blk;
+    const uint64_t local_items = n << log_blk, G = 1ULL << log_g;
     if (c.world == 1) {
-        // one rank: the local heap is the whole tree (its top 2n nodes double as the "replicated upper heap": same heap indices)
+        // one rank: the local heap is the whole tree; the mid and top heaps alias it (their indices are global heap indices then)
         DG_REQUIRE(local_items >= 2, "tree needs at least 2 items");
         local_nodes.alloc(local_items * 32);
         merkle_build(c, items_local_dev, local_nodes.p, local_items);
-        upper_p = local_nodes.p;
+        mid_p = top_p = local_nodes.p;
     } else {
+        DG_REQUIRE(n >= G && n % G == 0, "sharded tree needs at least one block per rank and k-range");
         const void *roots = items_local_dev;
         if (log_blk > 0) {
             local_nodes.alloc(local_items * 32);
             merkle_build_partial(c, items_local_dev, local_nodes.p, local_items, n);
-            roots = (const uint8_t *)local_nodes.p + n * 32;           // heap level with n nodes
+            roots = (const uint8_t *)local_nodes.p + n * 32;           // heap level with n nodes: the subtree roots, by k
         }
-        const uint64_t upper_level = n << log_g;
-        upper.alloc(2 * upper_level * 32);
-        DevBuf gathered(upper_level * 32);
-        comm_all_gather(c, roots, gathered.p, n * 32);
-        interleave_roots(c, gathered.p, upper.p, n, log_g);
-        merkle_finish(c, upper.p, upper_level);
-        upper_p = upper.p;
+        // re-shard the roots by k-range: recv[g'][k'] = root (k = g n/G + k') of rank g'
+        const uint64_t chunk = n / G;
+        DevBuf recv(n * 32);
+        comm_all_to_all(c, roots, recv.p, chunk * 32);
+        mid.alloc(2 * n * 32);
+        interleave_roots(c, recv.p, mid.p, chunk, log_g);           // mid[n + k' G + g'] : nodes [g n, (g + 1) n) of the global level n G
+        merkle_finish(c, mid.p, n);                                 // mid[1] = global node G + g
+        top.alloc(2 * G * 32);
+        comm_all_gather(c, (const uint8_t *)mid.p + 32, (uint8_t *)top.p + G * 32, 32);
+        merkle_finish(c, top.p, G);
+        mid_p = mid.p; top_p = top.p;
     }
     if (fetch_root) {
-        DG_CUDA(cudaMemcpyAsync(root.data(), (const uint8_t *)upper_p + 32, 32, cudaMemcpyDeviceToHost, c.stream));
+        DG_CUDA(cudaMemcpyAsync(root.data(), (const uint8_t *)top_p + 32, 32, cudaMemcpyDeviceToHost, c.stream));
         DG_CUDA(cudaStreamSynchronize(c.stream));
     }
-}
-
-std::vector<uint8_t> exchange_owned(Context &c, const void *d_local, size_t count, size_t item_bytes, const std::vector<int> &owners) {
-    std::vector<uint8_t> out(count * item_bytes);
-    if (count == 0) return out;
-    const size_t bytes = count * item_bytes;
-    DevBuf all(bytes * c.world);
-    comm_all_gather(c, d_local, all.p, bytes);
-    std::vector<uint8_t> host(bytes * c.world);
-    DG_CUDA(cudaMemcpyAsync(host.data(), all.p, host.size(), cudaMemcpyDeviceToHost, c.stream));
-    DG_CUDA(cudaStreamSynchronize(c.stream));
-    for (size_t q = 0; q < count; q++) {
-        const int o = owners[q] < 0 ? c.rank : owners[q];
-        memcpy(out.data() + q * item_bytes, host.data() + (size_t)o * bytes + q * item_bytes, item_bytes);
-    }
-    return out;
 }
 
 // out[t] = base_t ? ((const uint4 *)base_t)[unit_t] : 0
@@ -186,53 +180,6 @@ void FetchBatch::run() {
         const int o = owner_[t] < 0 ? c_.rank : owner_[t];
         memcpy(out_.data() + t * 16, host.data() + ((size_t)o * n + t) * 16, 16);
     }
-}
-
-static std::vector<Digest> fetch_digests(Context &c, const void *src_local, const std::vector<ShardLocation> &loc) {
-    const size_t count = loc.size();
-    std::vector<Digest> out(count);
-    if (count == 0) return out;
-    std::vector<uint64_t> idx(count);
-    std::vector<int> owners(count);
-    for (size_t q = 0; q < count; q++) { owners[q] = loc[q].owner; idx[q] = (loc[q].owner == c.rank) ? loc[q].index : 0; }
-    DevBuf d_idx(count * 8), d_out(count * 32);
-    DG_CUDA(cudaMemcpyAsync(d_idx.p, idx.data(), count * 8, cudaMemcpyHostToDevice, c.stream));
-    gather32(c, src_local, d_idx.as<unsigned long long>(), (int)count, d_out.p);
-    std::vector<uint8_t> bytes = exchange_owned(c, d_out.p, count, 32, owners);
-    memcpy(out.data(), bytes.data(), bytes.size());
-    return out;
-}
-
-std::vector<Digest> ShardedTree::fetch_nodes(Context &c, const std::vector<uint64_t> &heap_indices) const {
-    std::vector<Digest> out(heap_indices.size());
-    std::vector<uint64_t> up_idx;
-    std::vector<size_t> up_pos, lo_pos;
-    std::vector<ShardLocation> lo_loc;
-    for (size_t q = 0; q < heap_indices.size(); q++) {
-        ShardLocation l = geom.node(heap_indices[q]);
-        if (l.upper) { up_idx.push_back(l.index); up_pos.push_back(q); }
-        else { lo_loc.push_back(l); lo_pos.push_back(q); }
-    }
-    if (!up_idx.empty()) {   // replicated: purely local
-        DevBuf d_idx(up_idx.size() * 8), d_out(up_idx.size() * 32);
-        DG_CUDA(cudaMemcpyAsync(d_idx.p, up_idx.data(), up_idx.size() * 8, cudaMemcpyHostToDevice, c.stream));
-        gather32(c, upper_p, d_idx.as<unsigned long long>(), (int)up_idx.size(), d_out.p);
-        std::vector<Digest> got(up_idx.size());
-        DG_CUDA(cudaMemcpyAsync(got.data(), d_out.p, got.size() * 32, cudaMemcpyDeviceToHost, c.stream));
-        DG_CUDA(cudaStreamSynchronize(c.stream));
-        for (size_t i = 0; i < got.size(); i++) out[up_pos[i]] = got[i];
-    }
-    if (!lo_loc.empty()) {
-        std::vector<Digest> got = fetch_digests(c, local_nodes.p, lo_loc);
-        for (size_t i = 0; i < got.size(); i++) out[lo_pos[i]] = got[i];
-    }
-    return out;
-}
-
-std::vector<Digest> ShardedTree::fetch_items(Context &c, const std::vector<uint64_t> &item_indices) const {
-    std::vector<ShardLocation> loc;
-    for (uint64_t i : item_indices) loc.push_back(geom.item(i));
-    return fetch_digests(c, items_local, loc);
 }
 
 }  // namespace dg

@@ -1,10 +1,16 @@
-// Coset-sharded commitment trees and owner-based fetches (multi-GPU).
+// Coset-sharded commitment trees (multi-GPU).
 //
-// A committed matrix has its level-0 items (row hashes for the trace tree, first-level nodes for the constraint tree) indexed
-// i = (k * G + g) * blk + j : rank g owns, for every k < n, the aligned block of blk = 2^log_blk consecutive items.  Each
-// rank builds the n complete subtrees over its blocks, the n subtree roots per rank are all-gathered, interleaved into the
-// level with n*G nodes, and the upper tree is finished redundantly on every rank (so all ranks hold the same root).
-// With G == 1 the same code runs without communication.
+// A committed matrix has its level-0 items (row hashes for the trace tree, first-level nodes for the constraint tree, row hashes of a
+// FRI layer) indexed i = (k * G + g) * blk + j : rank g owns, for every k < n, the aligned block of blk = 2^log_blk consecutive items.
+//   local   each rank builds the n complete subtrees over its blocks (levels with more than n*G nodes);
+//   mid     the n*G subtree roots are re-sharded by k-range with one all-to-all (rank g receives the G roots of every k in
+//           [g n/G, (g+1) n/G): a contiguous run of n nodes of the global level n*G) and rank g builds the subtree over them -- the
+//           levels with G < m <= n*G nodes, each rank holding m/G consecutive nodes of every such level;
+//   top     the G mid-roots (32 bytes each) are all-gathered and the last log2(G) levels are hashed redundantly, so every rank
+//           holds the same root at the Fiat-Shamir point.
+// Per tree a rank moves (G-1)/G * 32 n bytes and hashes n blk + n nodes instead of all-gathering 32 n G bytes and hashing n G nodes
+// redundantly (r02, 8 GPUs, 2^25 rows: trace tree 1.08 ms with the replicated upper tree).  With G == 1 the same code runs without
+// communication and the three heaps are one.
 #pragma once
 #include <array>
 #include "common.cuh"
@@ -13,7 +19,8 @@ namespace dg {
 
 typedef std::array<uint8_t, 32> Digest;
 
-struct ShardLocation { int owner; bool upper; uint64_t index; };   // upper: index into the replicated upper heap, else local heap / item index
+enum { SHARD_LOCAL = 0, SHARD_TOP = 1, SHARD_MID = 2 };
+struct ShardLocation { int owner; int kind; uint64_t index; };   // kind: which heap `index` points into (SHARD_TOP: replicated, owner = -1)
 
 struct ShardGeom {
     uint64_t n;          // number of blocks per rank
@@ -60,28 +67,22 @@ struct ShardedTree {
     ShardGeom geom;
     const void *items_local = nullptr;   // n * blk digests, [k][j]
     DevBuf local_nodes;                  // heap over the local items (valid for levels with >= n nodes)
-    DevBuf upper;                        // replicated heap: 2 * n * G digests, level with n*G nodes at [nG, 2nG)
-    const void *upper_p = nullptr;       // the upper heap (one rank: the local heap itself)
+    DevBuf mid, top;                     // mid: heap over this rank's n nodes of the level n*G (2n digests); top: replicated heap of 2G digests
+    const void *mid_p = nullptr, *top_p = nullptr;     // one rank: both alias the local heap (global heap indices)
     Digest root;
 
     // fetch_root = false leaves the root on the device (upper_p + 32): no host synchronisation
     void build(Context &c, const void *items_local_dev, uint64_t n, int log_blk, bool fetch_root = true);
-    const void *root_dev() const { return (const uint8_t *)upper_p + 32; }
-    // collective fetches (every rank passes the same lists); results in request order
-    std::vector<Digest> fetch_nodes(Context &c, const std::vector<uint64_t> &heap_indices) const;
-    std::vector<Digest> fetch_items(Context &c, const std::vector<uint64_t> &item_indices) const;
-    // the same locations as references for a FetchBatch
+    const void *root_dev() const { return (const uint8_t *)top_p + 32; }
+    // locations as references for a FetchBatch
     FetchRef item_ref(uint64_t item_index) const { ShardLocation l = geom.item(item_index); return FetchRef{items_local, l.index, l.owner}; }
     FetchRef node_ref(uint64_t heap_index) const {
         ShardLocation l = geom.node(heap_index);
-        if (l.upper) return FetchRef{upper_p, l.index, -1};
+        if (l.kind == SHARD_TOP) return FetchRef{top_p, l.index, -1};
+        if (l.kind == SHARD_MID) return FetchRef{mid_p, l.index, l.owner};
         return FetchRef{local_nodes.p, l.index, l.owner};
     }
 };
-
-// owner-based exchange: every rank has filled `local` (count items of item_bytes) with the entries it owns; returns, for each
-// request q, the entry produced by owners[q]
-std::vector<uint8_t> exchange_owned(Context &c, const void *d_local, size_t count, size_t item_bytes, const std::vector<int> &owners);
 
 void merkle_build_partial(Context &c, const void *leaves, void *nodes, unsigned long long L, unsigned long long stop);
 void merkle_build(Context &c, const void *leaves, void *nodes, unsigned long long L);

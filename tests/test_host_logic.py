@@ -127,18 +127,19 @@ def test_periodic_tables_interpolate_the_round_constants(L):
 
 
 def test_sharded_tree_index_algebra(L):
-    """ShardGeom (distaff_b200/csrc/shard.cu) against a brute-force model: build the global heap of item ids and the per-rank local
-    heaps, then check that every global node / item is found at the location the product code computes."""
+    """ShardGeom (distaff_b200/csrc/shard.cu) against a brute-force model: build the global heap of item ids, the per-rank local heaps,
+    the per-rank mid heaps (subtree over the rank's k-range of the level with n*G nodes) and the replicated top heap, then check that
+    every global node / item is found at the location the product code computes."""
     import ctypes
     out = (ctypes.c_int64 * 3)()
-    for n, log_blk, log_g in ((4, 2, 1), (8, 3, 2), (4, 2, 3), (16, 0, 3), (8, 5, 0), (2, 1, 2)):
+    LOCAL, TOP, MID = 0, 1, 2
+    for n, log_blk, log_g in ((4, 2, 1), (8, 3, 2), (8, 2, 3), (16, 0, 3), (8, 5, 0), (4, 1, 2), (64, 2, 3)):
         blk, G = 1 << log_blk, 1 << log_g
         total = n * blk * G
         # global tree: node = frozenset of the level-0 items below it
         level = [frozenset([i]) for i in range(total)]
         glob = {}
         size = total
-        items_level = level
         while size > 1:
             level = [level[2 * i] | level[2 * i + 1] for i in range(size // 2)]
             size //= 2
@@ -155,16 +156,41 @@ def test_sharded_tree_index_algebra(L):
                 sz //= 2
                 for o, s_ in enumerate(lv):
                     heap[sz + o] = s_
-            local.append((its, heap))
+            local.append((its, heap, lv if blk > 1 else its))       # [2] = the n subtree roots, by k
+        # mid heaps: rank g gets, from every rank g', the roots of k in [g n/G, (g+1) n/G); node k'*G + g' of its level with n nodes
+        mid = []
+        for g in range(G):
+            chunk = n // G
+            lv = [None] * n
+            for g2 in range(G):
+                for k2 in range(chunk):
+                    lv[k2 * G + g2] = local[g2][2][g * chunk + k2]
+            heap = {n + o: s_ for o, s_ in enumerate(lv)}
+            sz = n
+            while sz > 1:
+                lv = [lv[2 * i] | lv[2 * i + 1] for i in range(sz // 2)]
+                sz //= 2
+                for o, s_ in enumerate(lv):
+                    heap[sz + o] = s_
+            mid.append(heap)
+        top = {G + g: mid[g][1] for g in range(G)}
+        lv, sz = [mid[g][1] for g in range(G)], G
+        while sz > 1:
+            lv = [lv[2 * i] | lv[2 * i + 1] for i in range(sz // 2)]
+            sz //= 2
+            for o, s_ in enumerate(lv):
+                top[sz + o] = s_
         for i in range(total):
             assert L.dg_host_shard_locate(n, log_blk, log_g, 0, i, out) == 0
-            owner, upper, idx = out[0], out[1], out[2]
-            assert upper == 0 and local[owner][0][idx] == frozenset([i])
+            owner, kind, idx = out[0], out[1], out[2]
+            assert kind == LOCAL and local[owner][0][idx] == frozenset([i])
         for h in range(1, total):
             assert L.dg_host_shard_locate(n, log_blk, log_g, 1, h, out) == 0
-            owner, upper, idx = out[0], out[1], out[2]
-            if upper:
-                assert h < 2 * n * G and idx == h
+            owner, kind, idx = out[0], out[1], out[2]
+            if kind == TOP:
+                assert owner == -1 and idx == h and top[idx] == glob[h]
+            elif kind == MID:
+                assert mid[owner][idx] == glob[h], (n, log_blk, log_g, h)
             else:
                 assert local[owner][1][idx] == glob[h], (n, log_blk, log_g, h)
 

@@ -1,7 +1,8 @@
 """world_size-2 checks on CPU (gloo) of the N > 1 path's host-side logic:
   * the coset-sharded commitment restated with numpy + the oracle's BLAKE3: each rank builds the subtrees
-    over the items it owns, roots are all-gathered and interleaved, the upper tree is finished redundantly -> same root and
-    same nodes as the unsharded tree, and dg_host_shard_locate (product code) points at the owner/local index of every node;
+    over the items it owns, the subtree roots are re-sharded by k-range (all-to-all), each rank builds the subtree over its n nodes of
+    the level n*G, the G mid-roots are all-gathered and the top is finished redundantly -> same root and same nodes as the unsharded
+    tree, and dg_host_shard_locate (product code) points at the owner / heap / index of every node;
   * bench.py --impl reference under torchrun: rank 0 alone prints the JSON line, the other rank exits 0."""
 import json
 import os
@@ -36,29 +37,47 @@ while size > n:
     size //= 2
     for o, d in enumerate(level):
         local_heap[size + o] = d
-roots = level                                                                       # n subtree roots of this rank
-gathered = [None] * G
-dist.all_gather_object(gathered, roots)
-upper = {}
-lvl = [gathered[g][k] for k in range(n) for g in range(G)]                          # interleave: index k*G + g
-size = n * G
+roots = level                                                                       # n subtree roots of this rank, by k
+chunk = n // G
+send = [roots[h * chunk:(h + 1) * chunk] for h in range(G)]                          # chunk h goes to rank h
+recv = [None] * G
+dist.all_to_all_object(recv, send) if hasattr(dist, "all_to_all_object") else None
+if recv[0] is None:                                                                 # gloo: emulate the all-to-all with an all-gather
+    everything = [None] * G
+    dist.all_gather_object(everything, send)
+    recv = [everything[g2][rank] for g2 in range(G)]
+mid = {}
+lvl = [recv[g2][k2] for k2 in range(chunk) for g2 in range(G)]                      # node k'*G + g' of my level with n nodes
+size = n
 for o, d in enumerate(lvl):
-    upper[size + o] = d
+    mid[size + o] = d
 while size > 1:
     lvl = [po.hash("blake3", lvl[2 * i] + lvl[2 * i + 1]) for i in range(size // 2)]
     size //= 2
     for o, d in enumerate(lvl):
-        upper[size + o] = d
-assert upper[1] == full[32:64], "sharded root differs"
+        mid[size + o] = d
+mid_roots = [None] * G
+dist.all_gather_object(mid_roots, mid[1])
+top = {G + g2: mid_roots[g2] for g2 in range(G)}
+lvl, size = mid_roots, G
+while size > 1:
+    lvl = [po.hash("blake3", lvl[2 * i] + lvl[2 * i + 1]) for i in range(size // 2)]
+    size //= 2
+    for o, d in enumerate(lvl):
+        top[size + o] = d
+assert top[1] == full[32:64], "sharded root differs"
 L = backend.lib()
 out = (ctypes.c_int64 * 3)()
 log_g = G.bit_length() - 1
 for h in range(1, total):
     assert L.dg_host_shard_locate(n, 2, log_g, 1, h, out) == 0
-    owner, is_upper, idx = out[0], out[1], out[2]
+    owner, kind, idx = out[0], out[1], out[2]
     want = full[32 * h: 32 * h + 32]
-    if is_upper:
-        assert upper[idx] == want
+    if kind == 1:
+        assert top[idx] == want
+    elif kind == 2:
+        if owner == rank:
+            assert mid[idx] == want
     elif owner == rank:
         assert local_heap[idx] == want
 for i in range(total):
