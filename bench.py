@@ -30,10 +30,33 @@ COLLATZ_START_2_20 = 6012607780440691934780549639      # 2600 Collatz steps, all
 METRIC = "prove ms for 2^20-step trace (default 120-bit ProofOptions)"
 
 
+def metric_name(log_n):
+    return METRIC if log_n == 20 else "prove ms for 2^%d-step trace (default 120-bit ProofOptions)" % log_n
+
+
 def collatz_start_for(log_n):
     """smallest-effort start values whose traces pad to 2^log_n steps (211 VM operations per Collatz iteration)"""
     table = {20: COLLATZ_START_2_20, 19: 93571393692802302, 18: 63728127, 17: 837799, 16: 6171, 15: 27, 14: 123, 13: 25, 12: 7}
     return table.get(log_n)
+
+
+def build_workload(args, log_n=None):
+    """--workload collatz (default, BASELINE configs[3]) | fibonacci (configs[1]: 2^16 steps) | merkle (configs[2]: 2^14 steps)"""
+    from distaff_b200 import hostvm
+    log_n = log_n or args.log_n
+    kind = getattr(args, "workload", "collatz")
+    if kind == "fibonacci":
+        n_terms = (1 << log_n) // 16 - 6
+        tr = hostvm.fibonacci(n_terms)
+        assert tr.length == 1 << log_n, tr.length
+        return tr, f"fibonacci({n_terms})"
+    if kind == "merkle":
+        count = {12: 1, 13: 2, 14: 4, 15: 8, 16: 16}.get(log_n)
+        assert count, "--workload merkle supports --log-n 12..16 (depth-64 paths, 2^12 steps each)"
+        tr = hostvm.merkle_paths(64, count)
+        assert tr.length == 1 << log_n, tr.length
+        return tr, f"merkle_paths(depth=64, count={count})"
+    return build_trace(log_n)
 
 
 def build_trace(log_n):
@@ -104,7 +127,9 @@ def peak_gbs():
 # -------------------------------------------------------------------------------------------------------------------------
 def oracle_threads():
     """threads for the CPU arm: all host threads unless BENCH_REF_THREADS says otherwise (1 = what the reference prover itself uses)"""
-    return max(1, int(os.environ.get("BENCH_REF_THREADS", os.cpu_count() or 1)))
+    # default: at most 32 -- on the 128-thread hosts of this pool the restatement is fastest there (2^16 steps: 25.7 s on 1 thread, 4.6 s on 8,
+    # 2.2 s on 32, 4.6 s on 64, 9.6 s on 128: profiles/r02_oracle_threads.txt)
+    return max(1, int(os.environ.get("BENCH_REF_THREADS", min(32, os.cpu_count() or 1))))
 
 
 STAGE_NAMES = ["extend trace", "trace merkle tree", "evaluate constraints", "combine constraint polys", "constraint lde + tree",
@@ -141,7 +166,7 @@ def run_reference(args):
     from oracle import pyoracle as po
     log_s = args.ref_log_n or args.log_n
     threads = po.set_threads(oracle_threads())
-    tr, name = build_trace(log_s)
+    tr, name = build_workload(args, log_s)
     budget_s = float(os.environ.get("BENCH_REF_BUDGET_S", "240"))
     times, stage_ms, proof = [], np.zeros(9), None
     t_start = time.perf_counter()
@@ -164,11 +189,11 @@ def run_reference(args):
             break
     value = float(np.mean(times))
     sha = hashlib.sha256(proof).hexdigest()
-    gold = golden_for(log_s)
+    gold = golden_for(log_s) if args.workload == "collatz" else None
     sample = (f"{name}: the full 2^{log_s}-step trace x {tr.width} registers proven {len(times)}x in {value:.0f} ms per proof on {threads} host threads "
               f"(same workload as the GPU arm, no scaling)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "ms", "n_gpus": args.gpus, "steps": len(times), "warmup": done_warm,
+        "impl": "reference", "metric": metric_name(log_s), "value": value, "unit": "ms", "n_gpus": args.gpus, "steps": len(times), "warmup": done_warm,
         "ms_per_step": value, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u128 (128-bit prime field) + u32 (blake3)",
         "data": "synthetic",
         "config": {"workload": workload_name(name, log_s, tr.width),
@@ -203,7 +228,7 @@ def run_ours(args):
     if world > 1:
         backend.comm_init_from_torch(dist, local_rank)
 
-    tr, name = build_trace(args.log_n)
+    tr, name = build_workload(args)
     n, w = tr.length, tr.width
     regs = np.ascontiguousarray(tr.registers)
     opts = dg.ProofOptions()
@@ -297,7 +322,7 @@ def run_ours(args):
     t_v = time.perf_counter()
     verdict = po.verify(tr.program_hash, tr.public_inputs, tr.outputs, proof.bytes)
     verify_ms = (time.perf_counter() - t_v) * 1e3
-    gold = golden_for(log_n_of(n))
+    gold = golden_for(log_n_of(n)) if args.workload == "collatz" else None
     trace_sha = hashlib.sha256(regs.tobytes()).hexdigest() if gold else None
     check = {"proof_sha256": proof_sha, "oracle_verifier": "accepted" if verdict is None else "REJECTED: %s" % verdict, "oracle_verify_ms": verify_ms,
              "all_ranks_same_proof": ranks_agree,
@@ -351,13 +376,13 @@ def run_ours(args):
     cpu = {"value": None, "unit": "ms", "cores": 1, "kind": "port", "sample": "skipped (--no-cpu-baseline)"}
     if not args.no_cpu_baseline and world == 1:
         threads = po.set_threads(oracle_threads())
-        tr14, _ = build_trace(14)
+        tr14, _ = build_workload(args, 14)
         t2 = time.perf_counter()
         r14 = po.prove(tr14.registers, tr14.ctx_depth, tr14.loop_depth, tr14.public_inputs, tr14.outputs)
         t14 = time.perf_counter() - t2
         assert r14.error is None
         log_s = args.ref_log_n or int(np.clip(14 + np.floor(np.log2(max(1.0, 20.0 / max(t14, 1e-3)))), 14, min(18, log_n)))
-        trs, sname = build_trace(log_s)
+        trs, sname = build_workload(args, log_s)
         t2 = time.perf_counter()
         r = po.prove(trs.registers, trs.ctx_depth, trs.loop_depth, trs.public_inputs, trs.outputs)
         cpu_ms = (time.perf_counter() - t2) * 1e3
@@ -373,7 +398,7 @@ def run_ours(args):
         po.set_threads(1)
 
     line = {
-        "metric": METRIC, "value": value, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(log_n), "value": value, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u128 (128-bit prime field) + u32 (blake3)", "data": "synthetic",
         "config": {"workload": workload_name(name, log_n, w),
@@ -395,6 +420,125 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+
+# -------------------------------------------------------------------------------------------------------------------------
+def run_microbench(args):
+    """BASELINE.json config 5: NTT / LDE / leaf-hash / Merkle sweeps on device-resident data (benches/fft.rs:6, benches/hash.rs:16-27 shapes).
+    Every rank runs the same sweep on its own GPU (independent vectors: the building blocks shard without any collective, "weak"
+    scaling); times are CUDA events on the library's stream, L2 flushed between iterations, max over ranks; aggregate GB/s = N x bytes /
+    max time.  Algorithmic bytes are SURVEY.md 8d's: NTT 32 n; LDE column 16 n + 16 N; leaf hash 16 w N + 32 N; tree 64 L.
+    Rank 0 also times the CPU oracle (all host threads) on the same shapes up to 2^20 elements."""
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ["DG_DEVICE"] = str(local_rank)
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from distaff_b200 import backend, felt
+    L = backend.lib()
+    info = backend.device_info()
+    peak, peak_kind = peak_gbs()
+    quick = args.quick
+    iters = 3 if quick else 5
+
+    def timed(fn):
+        ms = ctypes.c_float(0)
+        got = []
+        for i in range(iters + 2):
+            backend.check(L.dg_dev_flush_l2())
+            if dist is not None:
+                dist.barrier()
+            fn(ctypes.byref(ms))
+            if i >= 2:
+                got.append(ms.value)
+        med = float(np.median(got))
+        if dist is not None:
+            t = torch.tensor([med], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            med = float(t.item())
+        return med
+
+    po = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        threads = po.set_threads(oracle_threads())
+
+    def cpu_time(fn):
+        t0 = time.perf_counter()
+        fn()
+        return (time.perf_counter() - t0) * 1e3
+
+    rows = []
+
+    def emit(kind, shape, ms, alg_bytes, cpu_ms=None, extra=None):
+        gbs = world * alg_bytes / (ms * 1e-3) / 1e9
+        r = {"kernel": kind, "shape": shape, "ms": ms, "alg_gbs_aggregate": gbs, "alg_gbs_per_gpu": gbs / world, "frac_of_hbm_peak_per_gpu": gbs / world / peak,
+             "cpu_ms": cpu_ms, "speedup_vs_cpu": (world * cpu_ms / ms) if cpu_ms else None}
+        if extra:
+            r.update(extra)
+        rows.append(r)
+        if rank == 0 and args.verbose:
+            print("  %-10s %-28s %9.3f ms  %8.1f GB/s/GPU (%.1f%%)  cpu %s" % (kind, shape, ms, gbs / world, 100 * gbs / world / peak,
+                                                                              "%.0f ms" % cpu_ms if cpu_ms else "-"), file=sys.stderr, flush=True)
+
+    ntt_logs = (14, 18, 22) if quick else range(14, 25, 2)
+    for log_n in ntt_logs:
+        n = 1 << log_n
+        vals = felt.random_elements(n, log_n)
+        buf = backend.DeviceBuffer(n * 16).upload(vals)
+        ms = timed(lambda m: backend.check(L.dg_dev_ntt(buf.ptr, log_n, 1, 0, m)))
+        cpu = cpu_time(lambda: po.fft(vals)) if (po is not None and log_n <= 20) else None
+        emit("ntt", "2^%d elements" % log_n, ms, 32.0 * n, cpu)
+        buf.free()
+    lde_logs = (14, 18) if quick else (12, 14, 16, 18, 20)
+    for log_n in lde_logs:
+        w, n = 16, 1 << log_n
+        cols = felt.random_elements(w * n, 7)
+        polys = backend.DeviceBuffer(w * n * 16).upload(cols)
+        ext = backend.DeviceBuffer(w * n * 32 * 16)
+        ms = timed(lambda m: backend.check(L.dg_dev_lde(polys.ptr, ext.ptr, log_n, 5, w, m)))
+        cpu = None
+        if po is not None and log_n <= 16:
+            one = np.zeros((n * 32, 2), dtype=np.uint64)
+            one[:n] = cols[:n]
+            cpu = w * cpu_time(lambda: po.fft(one))           # one zero-padded column transform (trace_table.rs:165) x w columns
+        emit("lde x32", "%d columns x 2^%d" % (w, log_n), ms, w * (16.0 * n + 16.0 * n * 32), cpu)
+        leaves = backend.DeviceBuffer(n * 32 * 32)
+        ms = timed(lambda m: backend.check(L.dg_dev_hash_rows(ext.ptr, w, log_n, 5, leaves.ptr, m)))
+        emit("leaf hash", "2^%d rows x %d columns" % (log_n + 5, w), ms, 16.0 * w * n * 32 + 32.0 * n * 32)
+        nodes = backend.DeviceBuffer(n * 32 * 32)
+        ms = timed(lambda m: backend.check(L.dg_dev_merkle_build(leaves.ptr, n * 32, nodes.ptr, m)))
+        cpu = None
+        if po is not None and log_n + 5 <= 21:
+            lv = np.frombuffer(np.random.Generator(np.random.PCG64(log_n)).bytes(n * 32 * 32), dtype=np.uint8)
+            cpu = cpu_time(lambda: po.merkle_nodes("blake3", lv.tobytes()))
+        emit("merkle", "2^%d leaves (blake3)" % (log_n + 5), ms, 64.0 * n * 32, cpu)
+        for x in (polys, ext, leaves, nodes):
+            x.free()
+    if not quick:
+        for name, hid in (("rescue", 1), ("poseidon", 2)):
+            for log_l in (14, 18):
+                L_ = 1 << log_l
+                leaves = backend.DeviceBuffer(L_ * 32).upload(felt.random_elements(2 * L_, 7 + log_l))
+                nodes = backend.DeviceBuffer(L_ * 32)
+                ms = timed(lambda m: backend.check(L.dg_dev_merkle_build_with(hid, leaves.ptr, L_, nodes.ptr, m)))
+                emit("merkle", "2^%d leaves (%s)" % (log_l, name), ms, 64.0 * L_, None, {"hashes_per_s_aggregate": world * (L_ - 1) / (ms * 1e-3)})
+                leaves.free()
+                nodes.free()
+    out = {"microbench": rows, "n_gpus": world, "scaling": "weak", "device": info["name"], "hbm_peak_gbs": peak, "peak_kind": peak_kind,
+           "cpu": {"kind": "port", "cores": oracle_threads() if po is not None else None}, "timing": "CUDA events, L2 flushed, median of %d, max over ranks" % iters}
+    if po is not None:
+        po.set_threads(1)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -402,10 +546,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=20, help="log2 of the trace length (default: the 2^20-step headline workload)")
+    ap.add_argument("--workload", default="collatz", choices=["collatz", "fibonacci", "merkle"],
+                    help="collatz = the headline 2^20-step workload (default); fibonacci --log-n 16 and merkle --log-n 14 are BASELINE configs 2 and 3")
     ap.add_argument("--ref-log-n", type=int, default=0, help="log2 trace length of the CPU sample (default: chosen to fit the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--microbench", action="store_true", help="BASELINE config 5: NTT / LDE / leaf hash / Merkle sweep instead of the proof benchmark")
+    ap.add_argument("--quick", action="store_true", help="--microbench: three sizes only")
+    ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.microbench:
+        out = run_microbench(args)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -119,3 +119,36 @@ def collatz(start):
 def merkle_program(depth, index):
     """examples/merkle.rs:41-57"""
     return f"begin read.ab dup.2 smpath.{depth} swap.2 push.{index} roll.4 swap swap.2 pmpath.{depth} end"
+
+
+def merkle_paths(depth, count):
+    """`count` Merkle authentication paths of length `depth` verified back to back with the program of examples/merkle.rs:41-57 (paths
+    drawn from field::prng_vector with the example's seeds, path number in byte 3).  The example itself is capped at depth 64 = 2^12
+    steps by its own index arithmetic (examples/merkle.rs:75,106); four paths give BASELINE's 2^14-step Rescue-dominated trace."""
+    import ctypes
+    from .. import backend
+    L = backend.lib()
+
+    def prng_vector(seed, n):
+        out = np.zeros((n, 2), dtype=np.uint64)
+        backend.check(L.dg_host_prng_vector(bytes(seed), n, out.ctypes.data))
+        return felt.to_ints(out)
+
+    a_all, b_all, blocks = [], [], []
+    for c in range(count):
+        p0 = prng_vector(bytes([1, 2, 3, c] + [0] * 28), depth)
+        p1 = prng_vector(bytes([4, 5, 6, c] + [0] * 28), depth)
+        leaf_index = p0[0] % (2 ** (depth - 1))
+        a, b = [p0[0]], [p1[0]]
+        index = leaf_index + 2 ** (depth - 1)
+        for i in range(1, depth):
+            a += [0, p0[i]]
+            b += [index & 1, p1[i]]
+            index >>= 1
+        for i in range(1, depth):
+            a.append(p0[i])
+            b.append(p1[i])
+        a_all += a
+        b_all += b
+        blocks.append(f"read.ab dup.2 smpath.{depth} swap.2 push.{leaf_index} roll.4 swap swap.2 pmpath.{depth}")
+    return execute("begin " + " drop.4 ".join(blocks) + " end", secret_a=a_all, secret_b=b_all, num_outputs=4)
