@@ -90,6 +90,20 @@ def prove_device(d_registers, width, length, ctx_depth, loop_depth, public_input
     return _collect(handle, stats)
 
 
+def verify(program_hash, public_inputs, outputs, proof):
+    """distaff::verify (lib.rs:68-75 -> stark/verifier.rs:11-75) on the GPU.  Returns None when the proof is accepted, otherwise the
+    reference's error string (what `Err(msg)` carries); raises DgError for bytes that are not a serialized StarkProof."""
+    data = proof.bytes if isinstance(proof, StarkProof) else bytes(proof)
+    fi, fo = felt.from_ints(public_inputs), felt.from_ints(outputs)
+    msg = ctypes.create_string_buffer(256)
+    rc = backend.lib().dg_verify(bytes(program_hash), fi.ctypes.data, len(fi), fo.ctypes.data, len(fo), data, len(data), msg, 256)
+    if rc == 0:
+        return None
+    if rc == -6:
+        return msg.value.decode()
+    backend.check(rc)
+
+
 def execute(source, public_inputs=(), secret_a=(), secret_b=(), num_outputs=1, options=None):
     """distaff::execute (lib.rs:30-65): run the program on the host VM, then prove on the GPU. Returns (outputs, proof)."""
     trace = hostvm.execute(source, public_inputs, secret_a, secret_b, num_outputs)

@@ -49,6 +49,7 @@ EXPORTS = {
     "dg_device_info": [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_size_t)],
     "dg_prove": [ctypes.POINTER(DgTrace), vp, u32, vp, u32, ctypes.POINTER(DgOptions), ctypes.POINTER(vp), ctypes.POINTER(DgStats)],
     "dg_prove_device": [vp, u32, u64, u32, u32, vp, u32, vp, u32, ctypes.POINTER(DgOptions), ctypes.POINTER(vp), ctypes.POINTER(DgStats)],
+    "dg_verify": [vp, vp, u32, vp, u32, vp, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t],
     "dg_proof_serialized_len": [vp, ctypes.POINTER(ctypes.c_size_t)],
     "dg_proof_serialize": [vp, vp, ctypes.c_size_t],
     "dg_proof_digest": [vp, ctypes.c_int, vp],

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_kernel(cons
     for (int g = 0; g < 6; g++) acc.adj[g] = ZERO;
     acc.cA = P.coefA; acc.cB = P.coefB; acc.nonzero = false;
 
-    const fe *per = P.periodic + (s & 127ULL) * 23;                   // [ark_sponge 8][masks 3][ark_hasher 12]
+    const fe *per = P.per_override ? P.per_override : P.periodic + (s & 127ULL) * 23;     // [ark_sponge 8][masks 3][ark_hasher 12]
 
     DG_STEP();
     // ---- decoder: op bits (decoder/op_bits.rs:10-79), constraints 0..14 -------------------------------------------------------
@@ -484,9 +484,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_kernel(cons
     // ---- combine (evaluator.rs:335-358): result + sum_g adj_g * x^inc_g ------------------------------------------------------------------
     fe t_res = DG_REDUCE_WIDE(acc.res);
 #pragma unroll
-    for (int g = 0; g < 6; g++) t_res = fe_add(t_res, fe_mul(acc.adj[g], tw_pow(P.twN, lde_index * P.inc[g])));
+    for (int g = 0; g < 6; g++) t_res = fe_add(t_res, fe_mul(acc.adj[g], P.xpow_override ? P.xpow_override[g] : tw_pow(P.twN, lde_index * P.inc[g])));
     // on the trace domain (except its last step) every constraint must vanish (evaluator.rs:149-158)
-    if (c8 == 0 && k != n - 1) {
+    if (!P.verify_mode && c8 == 0 && k != n - 1) {
         if (acc.nonzero && live) atomicExch(P.violation, (unsigned)(k + 1));
         t_res = ZERO;
     }
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_smem_kernel
     for (int g = 0; g < 6; g++) acc.adj[g] = ZERO;
     acc.cA = P.coefA; acc.cB = P.coefB; acc.nonzero = false;
 
-    const fe *per = P.periodic + (s & 127ULL) * 23;                   // [ark_sponge 8][masks 3][ark_hasher 12]
+    const fe *per = P.per_override ? P.per_override : P.periodic + (s & 127ULL) * 23;     // [ark_sponge 8][masks 3][ark_hasher 12]
 
     DG_STEP();
     // ---- decoder: op bits (decoder/op_bits.rs:10-79), constraints 0..14 -------------------------------------------------------
@@ -915,9 +915,9 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_smem_kernel
     // ---- combine (evaluator.rs:335-358): result + sum_g adj_g * x^inc_g ------------------------------------------------------------------
     fe t_res = DG_REDUCE_WIDE(acc.res);
 #pragma unroll
-    for (int g = 0; g < 6; g++) t_res = fe_add(t_res, fe_mul(acc.adj[g], tw_pow(P.twN, lde_index * P.inc[g])));
+    for (int g = 0; g < 6; g++) t_res = fe_add(t_res, fe_mul(acc.adj[g], P.xpow_override ? P.xpow_override[g] : tw_pow(P.twN, lde_index * P.inc[g])));
     // on the trace domain (except its last step) every constraint must vanish (evaluator.rs:149-158)
-    if (c8 == 0 && k != n - 1) {
+    if (!P.verify_mode && c8 == 0 && k != n - 1) {
         if (acc.nonzero && live) atomicExch(P.violation, (unsigned)(k + 1));
         t_res = ZERO;
     }

@@ -17,6 +17,11 @@ struct AirParams {
     TwiddleRef twN;                     // powers of the LDE root w_N
     unsigned long long inc[6];          // incremental degrees of the groups 2,3,4,6,7,8  (evaluator.rs:395-402)
     unsigned *violation;                // set to step+1 when a trace-domain point violates a transition constraint
+    // verifier mode (verifier.cu): evaluate the transition combination at ONE out-of-domain point z -- the rows are (trace(z), trace(z g)),
+    // the periodic values are the cycle polynomials at z^(n/16) and the degree-adjustment powers z^inc_g come from the host
+    int verify_mode;
+    const fe *per_override;             // 23 values, or null
+    const fe *xpow_override;            // 6 values, or null
 };
 
 void launch_constraint_eval(Context &c, const AirParams &P);

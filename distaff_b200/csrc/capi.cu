@@ -332,6 +332,28 @@ int dg_set_rng_callbacks(const dg_rng_callbacks_t *callbacks) {
         fs::set_rng_hooks(&h);
     });
 }
+namespace dg {
+std::string verify_proof(Context &c, const uint8_t program_hash[32], const std::vector<fe> &inputs, const std::vector<fe> &outputs,
+                         const uint8_t *proof_bytes, size_t proof_len);
+}
+int dg_verify(const uint8_t program_hash[32], const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs,
+              const uint8_t *proof_bytes, size_t proof_len, char *message, size_t message_cap) {
+    if (message && message_cap) message[0] = 0;
+    return guarded([&] {
+        DG_REQUIRE(program_hash && proof_bytes, "null argument");
+        DG_REQUIRE((n_inputs == 0 || inputs16) && (n_outputs == 0 || outputs16), "null public inputs / outputs");
+        Context &c = ctx();
+        std::lock_guard<std::mutex> lk(c.mu);
+        std::vector<fe> in(n_inputs), out(n_outputs);
+        if (n_inputs) memcpy(in.data(), inputs16, n_inputs * 16);
+        if (n_outputs) memcpy(out.data(), outputs16, n_outputs * 16);
+        const std::string verdict = dg::verify_proof(c, program_hash, in, out, proof_bytes, proof_len);
+        if (!verdict.empty()) {
+            if (message && message_cap) { strncpy(message, verdict.c_str(), message_cap - 1); message[message_cap - 1] = 0; }
+            throw Error(DG_ERR_REJECTED, verdict);
+        }
+    });
+}
 int dg_proof_serialized_len(const dg_proof_t *proof, size_t *len) {
     return guarded([&] { DG_REQUIRE(proof && len, "null argument"); *len = ((const Proof *)proof)->bytes.size(); });
 }

@@ -207,7 +207,8 @@ std::vector<uint64_t> augmented_positions(const std::vector<uint64_t> &positions
 static fe g40() { return fe_make(0x86b8723e1920f4aaULL, 0x120532e7b364080aULL); }
 static fe root_of_unity(int log_order) { fe r = g40(); for (int i = 0; i < 40 - log_order; i++) r = fe_sqr(r); return r; }
 
-std::vector<fe> periodic_tables() {
+// the 23 periodic columns (sponge ARK 8 | masks 3 | hasher ARK 12) as polynomials of degree < 16 in y = x^(n/16): coefficient vectors
+static std::vector<std::vector<fe>> periodic_polys() {
     std::vector<std::vector<fe>> cols;
     auto add_table = [&](const unsigned long long (*t)[2], int ncols) {
         for (int c = 0; c < ncols; c++) {
@@ -226,25 +227,44 @@ std::vector<fe> periodic_tables() {
         cols.push_back(v);
     }
     add_table(DG_HASHER_ARK, 12);
-
-    const fe w16_inv = fe_inv(root_of_unity(4)), w128 = root_of_unity(7), inv16 = fe_inv(fe_make(16, 0));
-    std::vector<fe> p16(16), p128(128);
-    p16[0] = p128[0] = fe_make(1, 0);
+    const fe w16_inv = fe_inv(root_of_unity(4)), inv16 = fe_inv(fe_make(16, 0));
+    std::vector<fe> p16(16);
+    p16[0] = fe_make(1, 0);
     for (int i = 1; i < 16; i++) p16[i] = fe_mul(p16[i - 1], w16_inv);
-    for (int i = 1; i < 128; i++) p128[i] = fe_mul(p128[i - 1], w128);
-    std::vector<fe> out(128 * 23);
-    for (size_t c = 0; c < cols.size(); c++) {
-        fe poly[16];
+    std::vector<std::vector<fe>> polys(cols.size(), std::vector<fe>(16));
+    for (size_t c = 0; c < cols.size(); c++)
         for (int k = 0; k < 16; k++) {                       // inverse DFT: cycle values -> coefficients
             fe acc = fe_make(0, 0);
             for (int r = 0; r < 16; r++) acc = fe_add(acc, fe_mul(cols[c][r], p16[(r * k) & 15]));
-            poly[k] = fe_mul(acc, inv16);
+            polys[c][k] = fe_mul(acc, inv16);
         }
+    return polys;
+}
+
+std::vector<fe> periodic_tables() {
+    const std::vector<std::vector<fe>> polys = periodic_polys();
+    const fe w128 = root_of_unity(7);
+    std::vector<fe> p128(128);
+    p128[0] = fe_make(1, 0);
+    for (int i = 1; i < 128; i++) p128[i] = fe_mul(p128[i - 1], w128);
+    std::vector<fe> out(128 * 23);
+    for (size_t c = 0; c < polys.size(); c++)
         for (int s = 0; s < 128; s++) {                      // evaluate on the 8x extended cycle
             fe acc = fe_make(0, 0);
-            for (int k = 0; k < 16; k++) acc = fe_add(acc, fe_mul(poly[k], p128[(s * k) & 127]));
+            for (int k = 0; k < 16; k++) acc = fe_add(acc, fe_mul(polys[c][k], p128[(s * k) & 127]));
             out[(size_t)s * 23 + c] = acc;
         }
+    return out;
+}
+
+// the same 23 columns at an arbitrary point: y = x^(trace_length / 16)  (decoder/mod.rs evaluate_at, stack/mod.rs evaluate_at)
+std::vector<fe> periodic_at(fe y) {
+    const std::vector<std::vector<fe>> polys = periodic_polys();
+    std::vector<fe> out(23);
+    for (size_t c = 0; c < polys.size(); c++) {
+        fe acc = fe_make(0, 0);
+        for (int k = 15; k >= 0; k--) acc = fe_add(fe_mul(acc, y), polys[c][k]);
+        out[c] = acc;
     }
     return out;
 }

@@ -70,6 +70,7 @@ std::vector<uint64_t> augmented_positions(const std::vector<uint64_t> &positions
 
 // periodic tables of the evaluation domain: 128 rows x 23 columns (sponge ARK 8 | masks 3 | hasher ARK 12)
 std::vector<fe> periodic_tables();
+std::vector<fe> periodic_at(fe y);          // the 23 columns at y = x^(n/16) for an arbitrary x (verifier)
 
 // ---- batch Merkle proof planning ----------------------------------------------------------------------------------------
 struct NodeRef { bool leaf; uint64_t index; };

@@ -30,6 +30,7 @@ extern "C" {
 #define DG_ERR_NO_DEVICE (-3)    /* no CUDA device: this backend has no CPU path */
 #define DG_ERR_EXHAUSTED (-4)    /* PoW / query-position search exhausted (utils/mod.rs:39-41 panics in the reference) */
 #define DG_ERR_UNSATISFIED (-5)  /* transition constraints do not vanish on the trace (evaluator.rs:152-157 panics) */
+#define DG_ERR_REJECTED (-6)     /* dg_verify: the proof was rejected; the message is the reference's Err(String) (verifier.rs:28-73) */
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------- */
 int dg_init(int device);                     /* optional; device < 0 = $DG_DEVICE or 0 */
@@ -91,6 +92,15 @@ int dg_proof_serialize(const dg_proof_t *proof, uint8_t *buf, size_t cap);
 int dg_proof_digest(const dg_proof_t *proof, int which, uint8_t out32[32]);
 int dg_proof_pow_nonce(const dg_proof_t *proof, uint64_t *nonce);
 void dg_proof_free(dg_proof_t *proof);
+
+/* ---- the step after the path: stark::verify (verifier.rs:11-75) on the GPU -------------------------------------------------------
+ * Checks StarkProof bytes (the bincode encoding dg_proof_serialize emits / main.rs:45 writes) against a program hash and public
+ * inputs / outputs.  Returns DG_OK when the reference would return Ok(true); DG_ERR_REJECTED when it would return Err(msg), with msg
+ * copied to `message` (NUL-terminated, truncated to message_cap) and available from dg_last_error(); DG_ERR_INVALID for bytes that do
+ * not deserialize.  Hashing, Merkle batch verification, the constraint evaluation at z, the DEEP composition at the query positions
+ * and the FRI row folds run on the device (verifier.cu); the Fiat-Shamir draws use the same generator / callbacks as dg_prove. */
+int dg_verify(const uint8_t program_hash[32], const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs,
+              const uint8_t *proof_bytes, size_t proof_len, char *message, size_t message_cap);
 
 /* ---- building blocks (micro-benchmarks of BASELINE.json config 5; same kernels the prover uses) ---------------------- */
 /* math::fft / polynom::{eval_fft, interpolate_fft} (polynom.rs:23-28,82-86): natural-order DFT of `batch` vectors of 2^log_n
