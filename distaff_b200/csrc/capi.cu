@@ -14,6 +14,11 @@ void pow_hash(const uint8_t seed[32], unsigned long long nonce, uint8_t out[32])
 void hash_rows_plain(Context &c, const fe *cols, void *digests, int w, unsigned long long rows);
 }  // namespace dg
 
+namespace dg {
+std::string verify_proof(Context &c, const uint8_t program_hash[32], const std::vector<fe> &inputs, const std::vector<fe> &outputs,
+                         const uint8_t *proof_bytes, size_t proof_len);
+}
+
 using namespace dg;
 
 static thread_local std::string t_last_error;
@@ -331,10 +336,6 @@ int dg_set_rng_callbacks(const dg_rng_callbacks_t *callbacks) {
         fs::RngHooks h{callbacks->user, callbacks->draw_field, callbacks->draw_positions};
         fs::set_rng_hooks(&h);
     });
-}
-namespace dg {
-std::string verify_proof(Context &c, const uint8_t program_hash[32], const std::vector<fe> &inputs, const std::vector<fe> &outputs,
-                         const uint8_t *proof_bytes, size_t proof_len);
 }
 int dg_verify(const uint8_t program_hash[32], const uint8_t *inputs16, uint32_t n_inputs, const uint8_t *outputs16, uint32_t n_outputs,
               const uint8_t *proof_bytes, size_t proof_len, char *message, size_t message_cap) {
