@@ -45,6 +45,7 @@ class DgRngCallbacks(ctypes.Structure):
 
 EXPORTS = {
     "dg_init": [ctypes.c_int],
+    "dg_init_devices": [ctypes.c_int],
     "dg_set_rng_callbacks": [ctypes.POINTER(DgRngCallbacks)],
     "dg_device_info": [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_size_t)],
     "dg_prove": [ctypes.POINTER(DgTrace), vp, u32, vp, u32, ctypes.POINTER(DgOptions), ctypes.POINTER(vp), ctypes.POINTER(DgStats)],

@@ -27,9 +27,8 @@ namespace dg {
 
 __constant__ fe c_sponge_mds[16], c_sponge_inv_mds[16], c_hasher_mds[36], c_hasher_inv_mds[36];
 
-void air_upload_constants() {
-    static bool done = false;
-    if (done) return;
+void air_upload_constants(Context &c) {
+    if (c.air_consts) return;
     auto conv = [](const unsigned long long (*t)[2], int n, std::vector<fe> &out) {
         out.resize(n);
         for (int i = 0; i < n; i++) out[i] = fe_make(t[i][0], t[i][1]);
@@ -39,7 +38,7 @@ void air_upload_constants() {
     conv(DG_SPONGE_INV_MDS, 16, v);  DG_CUDA(cudaMemcpyToSymbol(c_sponge_inv_mds, v.data(), 16 * sizeof(fe)));
     conv(DG_HASHER_MDS, 36, v);      DG_CUDA(cudaMemcpyToSymbol(c_hasher_mds, v.data(), 36 * sizeof(fe)));
     conv(DG_HASHER_INV_MDS, 36, v);  DG_CUDA(cudaMemcpyToSymbol(c_hasher_inv_mds, v.data(), 36 * sizeof(fe)));
-    done = true;
+    c.air_consts = true;
 }
 
 __device__ __forceinline__ fe tw_pow(const TwiddleRef &t, unsigned long long e) {
@@ -941,7 +940,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_smem_kernel
 #undef ncf
 
 void launch_constraint_eval(Context &c, const AirParams &P) {
-    air_upload_constants();
+    air_upload_constants(c);
     const unsigned long long E = (unsigned long long)P.num_c8 << P.log_n;
     static int variant = -1;
     if (variant < 0) { const char *e = getenv("DG_AIR_CFG"); variant = e ? atoi(e) : 6; }
@@ -950,8 +949,7 @@ void launch_constraint_eval(Context &c, const AirParams &P) {
     do {                                                                                                                             \
         const size_t smem = (size_t)(P.w - ((DEC) ? 0 : 15)) * (BLOCK + 1) * sizeof(fe);                                             \
         auto k = constraint_eval_smem_kernel<BLOCK, MINB, DEC>;                                                                      \
-        static size_t attr = 0;                                                                                                      \
-        if (smem > attr) { DG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; } \
+        set_func_smem(c, (const void *)k, smem);                                                                                     \
         k<<<(unsigned)(E / BLOCK), BLOCK, smem, c.stream>>>(P);                                                                      \
     } while (0)
     int v = variant;

@@ -23,15 +23,14 @@ namespace dg {
 __constant__ fe c_alg_mds[36];
 __constant__ fe c_alg_ark[546];
 
-static void alg_upload_constants() {
-    static bool done = false;
-    if (done) return;
+static void alg_upload_constants(Context &c) {
+    if (c.alghash_consts) return;
     std::vector<fe> v(546);
     for (int i = 0; i < 36; i++) v[i] = fe_make(DG_HASH_MDS[i][0], DG_HASH_MDS[i][1]);
     DG_CUDA(cudaMemcpyToSymbol(c_alg_mds, v.data(), 36 * sizeof(fe)));
     for (int i = 0; i < 546; i++) v[i] = fe_make(DG_HASH_ARK[i][0], DG_HASH_ARK[i][1]);
     DG_CUDA(cudaMemcpyToSymbol(c_alg_ark, v.data(), 546 * sizeof(fe)));
-    done = true;
+    c.alghash_consts = true;
 }
 
 __device__ __forceinline__ void alg_add_constants(fe st[6], int off) {
@@ -122,7 +121,7 @@ __global__ void __launch_bounds__(128) alg_hash64_kernel(const uint4 *__restrict
 void alg_hash64(Context &c, int hash_id, const void *in, void *out, unsigned long long n) {
     DG_REQUIRE(hash_id >= 0 && hash_id <= 2, "hash id must be 0 (blake3), 1 (rescue) or 2 (poseidon)");
     if (n == 0) return;
-    alg_upload_constants();
+    alg_upload_constants(c);
     const unsigned grid = (unsigned)((n + 127) / 128);
     switch (hash_id) {
         case 0: alg_hash64_kernel<0><<<grid, 128, 0, c.stream>>>((const uint4 *)in, (uint4 *)out, n); break;

@@ -5,6 +5,7 @@
 #include "host_fs.h"
 #include "shard.h"
 #include "poly.h"
+#include <thread>
 
 namespace dg {
 void hash_trace_rows(Context &c, const fe *ext, void *leaves, int w, int log_n, int log_blowup);
@@ -107,9 +108,44 @@ __global__ void fill_kernel(uint4 *p, size_t n, unsigned v) {
     if (i < n) p[i] = make_uint4(v, v + 1, v + 2, v + 3);
 }
 
+// Single-process multi-GPU (dg_init_devices): the proof is sharded exactly as in the one-process-per-GPU mode, but the ranks are host
+// threads of this process, each bound to its own device context and NCCL communicator.  Rank 0 runs on the calling thread.
+template <typename F>
+static Proof *prove_on_all_devices(F &&prove_rank, dg_prove_stats_t *stats) {
+    const int n = ctx_device_count();
+    std::vector<Proof *> res(n, nullptr);
+    std::vector<int> codes(n, 0);
+    std::vector<std::string> msgs(n);
+    auto run = [&](int g) {
+        try {
+            Context &cg = ctx_of(g);
+            ctx_bind(&cg);
+            res[g] = prove_rank(cg, g == 0 ? stats : nullptr);
+        } catch (const dg::Error &e) { codes[g] = e.code; msgs[g] = e.what(); }
+        catch (const std::exception &e) { codes[g] = DG_ERR_INVALID; msgs[g] = e.what(); }
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < n; g++) th.emplace_back(run, g);
+    run(0);
+    for (auto &t : th) t.join();
+    ctx_bind(&ctx_of(0));
+    for (int g = 0; g < n; g++)
+        if (codes[g] != 0) {
+            for (auto *p : res) delete p;
+            throw Error(codes[g], "rank " + std::to_string(g) + ": " + msgs[g]);
+        }
+    for (int g = 1; g < n; g++) {
+        const bool same = res[g] && res[g]->bytes == res[0]->bytes;
+        delete res[g];
+        if (!same) { delete res[0]; throw Error(DG_ERR_CUDA, "ranks produced different proofs"); }
+    }
+    return res[0];
+}
+
 extern "C" {
 
 int dg_init(int device) { return guarded([&] { ctx_init(device); }); }
+int dg_init_devices(int n_devices) { return guarded([&] { ctx_init_devices(n_devices); }); }
 const char *dg_last_error(void) { return t_last_error.c_str(); }
 
 int dg_device_info(char *name, size_t cap, int *sm_count, size_t *total_mem) {
@@ -136,10 +172,9 @@ int dg_dev_sync(void) { return guarded([&] { DG_CUDA(cudaStreamSynchronize(ctx()
 int dg_dev_flush_l2(void) {
     return guarded([&] {
         Context &c = ctx();
-        static DevBuf scratch;
         const size_t bytes = (size_t)256 << 20;
-        scratch.ensure(bytes, true);
-        fill_kernel<<<(unsigned)(bytes / 16 / 256), 256, 0, c.stream>>>(scratch.as<uint4>(), bytes / 16, 7u); c.launches++;
+        c.l2_scratch.ensure(bytes, true);
+        fill_kernel<<<(unsigned)(bytes / 16 / 256), 256, 0, c.stream>>>(c.l2_scratch.as<uint4>(), bytes / 16, 7u); c.launches++;
         DG_CUDA(cudaGetLastError());
         DG_CUDA(cudaStreamSynchronize(c.stream));
     });
@@ -314,8 +349,14 @@ int dg_prove(const dg_trace_t *trace, const uint8_t *inputs16, uint32_t n_inputs
              const dg_options_t *options, dg_proof_t **proof_out, dg_prove_stats_t *stats) {
     return guarded([&] {
         DG_REQUIRE(trace && options && proof_out, "null argument");
+        DG_REQUIRE((n_inputs == 0 || inputs16) && (n_outputs == 0 || outputs16), "null public inputs / outputs");
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
+        if (ctx_device_count() > 1) {
+            *proof_out = (dg_proof_t *)prove_on_all_devices([&](Context &cg, dg_prove_stats_t *st) {
+                return prove_host(cg, *trace, inputs16, n_inputs, outputs16, n_outputs, *options, st); }, stats);
+            return;
+        }
         *proof_out = (dg_proof_t *)prove_host(c, *trace, inputs16, n_inputs, outputs16, n_outputs, *options, stats);
     });
 }
@@ -324,8 +365,15 @@ int dg_prove_device(const void *d_registers, uint32_t width, uint64_t length, ui
                     const dg_options_t *options, dg_proof_t **proof_out, dg_prove_stats_t *stats) {
     return guarded([&] {
         DG_REQUIRE(d_registers && options && proof_out, "null argument");
+        DG_REQUIRE((n_inputs == 0 || inputs16) && (n_outputs == 0 || outputs16), "null public inputs / outputs");
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
+        if (ctx_device_count() > 1) {          // the trace lives on device 0; the other devices read their columns over NVLink (peer access)
+            *proof_out = (dg_proof_t *)prove_on_all_devices([&](Context &cg, dg_prove_stats_t *st) {
+                return prove_device(cg, (const fe *)d_registers, width, length, ctx_depth, loop_depth, inputs16, n_inputs, outputs16, n_outputs, *options,
+                                    st, 0.0f); }, stats);
+            return;
+        }
         *proof_out = (dg_proof_t *)prove_device(c, (const fe *)d_registers, width, length, ctx_depth, loop_depth, inputs16, n_inputs, outputs16,
                                                 n_outputs, *options, stats, 0.0f);
     });

@@ -30,7 +30,7 @@ struct Nccl {
     fn_SendRecv Send = nullptr, Recv = nullptr;
     fn_Group GroupStart = nullptr, GroupEnd = nullptr;
     fn_GetErrorString GetErrorString = nullptr;
-    ncclComm_t comm = nullptr;
+    int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
 } g_nccl;
 
 void load_nccl() {
@@ -54,6 +54,7 @@ void load_nccl() {
     g_nccl.GroupStart = (fn_Group)sym("ncclGroupStart");
     g_nccl.GroupEnd = (fn_Group)sym("ncclGroupEnd");
     g_nccl.GetErrorString = (fn_GetErrorString)sym("ncclGetErrorString");
+    g_nccl.CommInitAll = (int (*)(ncclComm_t *, int, const int *))sym("ncclCommInitAll");
 }
 void nccl_check(int rc, const char *what) {
     if (rc != 0) throw Error(-2, std::string("NCCL ") + what + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
@@ -74,14 +75,26 @@ void comm_init(Context &c, int rank, int world, const uint8_t id_bytes[128]) {
         load_nccl();
         ncclUniqueId id;
         memcpy(id.internal, id_bytes, 128);
-        nccl_check(g_nccl.CommInitRank(&g_nccl.comm, world, id, rank), "ncclCommInitRank");
+        if (c.nccl_comm) { g_nccl.CommDestroy(c.nccl_comm); c.nccl_comm = nullptr; }      // a second dg_comm_init replaces the communicator
+        nccl_check(g_nccl.CommInitRank(&c.nccl_comm, world, id, rank), "ncclCommInitRank");
     }
     c.rank = rank;
     c.world = world;
 }
 
+// single process, one context per device: one communicator per context, created together
+void comm_init_all(std::vector<Context *> &ctxs) {
+    load_nccl();
+    const int n = (int)ctxs.size();
+    std::vector<ncclComm_t> comms(n);
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; i++) devs[i] = ctxs[i]->device;
+    nccl_check(g_nccl.CommInitAll(comms.data(), n, devs.data()), "ncclCommInitAll");
+    for (int i = 0; i < n; i++) { ctxs[i]->nccl_comm = comms[i]; ctxs[i]->rank = i; ctxs[i]->world = n; }
+}
+
 void comm_finalize(Context &c) {
-    if (g_nccl.comm) { g_nccl.CommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
+    if (c.nccl_comm) { g_nccl.CommDestroy(c.nccl_comm); c.nccl_comm = nullptr; }
     c.rank = 0;
     c.world = 1;
 }
@@ -92,7 +105,7 @@ void comm_all_gather(Context &c, const void *send, void *recv, size_t bytes) {
         if (send != recv) DG_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, c.stream));
         return;
     }
-    nccl_check(g_nccl.AllGather(send, recv, bytes, /*ncclUint8*/ 1, g_nccl.comm, c.stream), "ncclAllGather");
+    nccl_check(g_nccl.AllGather(send, recv, bytes, /*ncclUint8*/ 1, (ncclComm_t)c.nccl_comm, c.stream), "ncclAllGather");
 }
 
 // recv[g] (bytes each) = the chunk rank g sent to this rank; send[h] = the chunk for rank h.  One grouped send/recv per peer.
@@ -103,8 +116,8 @@ void comm_all_to_all(Context &c, const void *send, void *recv, size_t bytes) {
     }
     nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
     for (int p = 0; p < c.world; p++) {
-        nccl_check(g_nccl.Send((const uint8_t *)send + (size_t)p * bytes, bytes, /*ncclUint8*/ 1, p, g_nccl.comm, c.stream), "ncclSend");
-        nccl_check(g_nccl.Recv((uint8_t *)recv + (size_t)p * bytes, bytes, /*ncclUint8*/ 1, p, g_nccl.comm, c.stream), "ncclRecv");
+        nccl_check(g_nccl.Send((const uint8_t *)send + (size_t)p * bytes, bytes, /*ncclUint8*/ 1, p, (ncclComm_t)c.nccl_comm, c.stream), "ncclSend");
+        nccl_check(g_nccl.Recv((uint8_t *)recv + (size_t)p * bytes, bytes, /*ncclUint8*/ 1, p, (ncclComm_t)c.nccl_comm, c.stream), "ncclRecv");
     }
     nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
 }
@@ -112,7 +125,7 @@ void comm_all_to_all(Context &c, const void *send, void *recv, size_t bytes) {
 // in-place max over ranks of `count` uint32 values
 void comm_all_reduce_max_u32(Context &c, unsigned *buf, size_t count) {
     if (c.world == 1) return;
-    nccl_check(g_nccl.AllReduce(buf, buf, count, /*ncclUint32*/ 3, /*ncclMax*/ 2, g_nccl.comm, c.stream), "ncclAllReduce");
+    nccl_check(g_nccl.AllReduce(buf, buf, count, /*ncclUint32*/ 3, /*ncclMax*/ 2, (ncclComm_t)c.nccl_comm, c.stream), "ncclAllReduce");
 }
 
 }  // namespace dg

@@ -30,7 +30,7 @@ struct Error : public std::runtime_error {
         if (!(cond)) throw dg::Error(-1, std::string(msg));        \
     } while (0)
 
-// stream on which DevBuf allocations are ordered (the context's stream once it exists)
+// stream on which DevBuf allocations are ordered: the stream of the calling thread's current context
 cudaStream_t &alloc_stream();
 
 // Per-proof arena: a proof's buffers (tens of GB at 2^20 steps) are carved out of one device allocation with a bump pointer, so a
@@ -109,6 +109,12 @@ struct TwiddleRef {
 
 struct Context {
     int device = 0;
+    Arena arena;                            // per-proof bump arena of this device
+    void *nccl_comm = nullptr;              // this rank's NCCL communicator (comm.cu), one per context
+    DevBuf d_periodic;                      // periodic AIR tables on this device (prover.cu stage 3)
+    bool air_consts = false, alghash_consts = false;     // __constant__ tables uploaded to this device
+    std::map<const void *, size_t> func_smem;            // per-device cudaFuncSetAttribute(MaxDynamicSharedMemorySize) already applied
+    DevBuf l2_scratch;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;     // host->device uploads that overlap compute (prover.cu stage 1)
@@ -141,8 +147,16 @@ struct Context {
     const fe *roots(int log_l, bool inverse) const { return small_roots[inverse ? 1 : 0].as<fe>() + small_root_offset[log_l]; }
 };
 
-Context &ctx();              // lazily initialised singleton (device 0 or $DG_DEVICE / dg_init)
+// The calling thread's current context.  A process normally has one (device 0 or $DG_DEVICE / dg_init), created lazily; after
+// dg_init_devices(n) there is one context per device and dg_prove drives them from n host threads, each bound to its own.
+Context &ctx();
 void ctx_init(int device);
+void ctx_init_devices(int n);               // contexts for devices 0 .. n-1 + one NCCL communicator per device (single-process multi-GPU)
+int ctx_device_count();                     // number of contexts (1 unless ctx_init_devices was called)
+Context &ctx_of(int index);
+void ctx_bind(Context *c);                  // makes c the calling thread's current context (and its device current)
+// raises the dynamic shared-memory limit of a kernel on c's device once
+void set_func_smem(Context &c, const void *func, size_t bytes);
 
 // host-side field helpers (portable path of fp128.cuh)
 fe host_root_of_unity(int log_order);            // w of order 2^log_order  (field::get_root_of_unity)
@@ -164,6 +178,7 @@ void lde_batch(Context &c, const fe *src, fe *dst, int log_n, int log_blowup, in
 // ---- multi-GPU plumbing (comm.cu) -----------------------------------------------------------------------------------------
 void comm_unique_id(uint8_t out[128]);
 void comm_init(Context &c, int rank, int world, const uint8_t id_bytes[128]);
+void comm_init_all(std::vector<Context *> &ctxs);     // single process: ncclCommInitAll over the contexts' devices
 void comm_finalize(Context &c);
 void comm_all_gather(Context &c, const void *send, void *recv, size_t bytes_per_rank);
 void comm_all_to_all(Context &c, const void *send, void *recv, size_t bytes_per_peer);

@@ -22,21 +22,19 @@ __global__ void power_table_kernel(fe *out, fe step, unsigned count) {
     if (i < count) out[i] = fe_pow_u64(step, i);
 }
 
-static cudaStream_t g_alloc_stream = nullptr;
-cudaStream_t &alloc_stream() { return g_alloc_stream; }
-
-static Arena g_arena;
-Arena &arena() { return g_arena; }
+static thread_local Context *tl_ctx = nullptr;
+cudaStream_t &alloc_stream() { return ctx().stream; }
+Arena &arena() { return ctx().arena; }
 
 ArenaScope::ArenaScope() {
-    Arena &a = g_arena;
+    Arena &a = arena();
     a.off = 0;
     a.counted = 0;
     a.counting = true;
     a.active = a.base != nullptr && !getenv("DG_NO_ARENA");
 }
 ArenaScope::~ArenaScope() {
-    Arena &a = g_arena;
+    Arena &a = arena();
     a.counting = false;
     const bool overflowed = a.counted > a.cap;
     a.active = false;
@@ -55,11 +53,10 @@ ArenaScope::~ArenaScope() {
     }
 }
 
-static std::once_flag g_once;
-static Context *g_ctx = nullptr;
-static int g_device = -1;
+static std::mutex g_ctx_mu;
+static std::vector<Context *> g_ctxs;            // [0] = primary context; more after ctx_init_devices
 
-static void build_context(int device) {
+static Context *build_context(int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -68,12 +65,13 @@ static void build_context(int device) {
     DG_CUDA(cudaSetDevice(device));
     Context *c = new Context();
     c->device = device;
+    Context *prev = tl_ctx;
+    tl_ctx = c;                                          // the allocations below are ordered on this context's stream
     cudaDeviceProp prop;
     DG_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     DG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    g_alloc_stream = c->stream;
     {   // keep freed blocks in the pool instead of returning them to the driver between proofs
         cudaMemPool_t pool;
         DG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -103,25 +101,72 @@ static void build_context(int device) {
         }
     }
     DG_CUDA(cudaStreamSynchronize(c->stream));
-    g_ctx = c;
+    tl_ctx = prev;
+    return c;
 }
 
 void ctx_init(int device) {
-    std::call_once(g_once, [&]() {
-        if (device < 0) {
-            const char *env = getenv("DG_DEVICE");
-            device = env ? atoi(env) : 0;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        if (g_ctxs.empty()) {
+            if (device < 0) {
+                const char *env = getenv("DG_DEVICE");
+                device = env ? atoi(env) : 0;
+            }
+            g_ctxs.push_back(build_context(device));
+        } else if (device >= 0 && device != g_ctxs[0]->device) {
+            // a late dg_init(other device) must not silently keep the old device (every rank of a multi-GPU host would share one GPU)
+            throw Error(-1, "the library is already initialised on device " + std::to_string(g_ctxs[0]->device) + "; cannot switch to device " +
+                                std::to_string(device));
         }
-        g_device = device;
-        build_context(device);
-    });
-    if (!g_ctx) throw Error(-3, "CUDA context initialisation failed earlier in this process");
-    DG_CUDA(cudaSetDevice(g_ctx->device));
+    }
+    if (!tl_ctx) tl_ctx = g_ctxs[0];
+    DG_CUDA(cudaSetDevice(tl_ctx->device));
 }
 
 Context &ctx() {
+    if (!tl_ctx) ctx_init(-1);
+    else cudaSetDevice(tl_ctx->device);                  // the host may have switched the thread's device (e.g. another library)
+    return *tl_ctx;
+}
+
+void ctx_bind(Context *c) {
+    tl_ctx = c;
+    if (c) DG_CUDA(cudaSetDevice(c->device));
+}
+int ctx_device_count() { std::lock_guard<std::mutex> lk(g_ctx_mu); return (int)std::max<size_t>(1, g_ctxs.size()); }
+Context &ctx_of(int index) { std::lock_guard<std::mutex> lk(g_ctx_mu); DG_REQUIRE(index >= 0 && index < (int)g_ctxs.size(), "no such device context"); return *g_ctxs[index]; }
+
+void ctx_init_devices(int n) {
+    DG_REQUIRE(n == 1 || n == 2 || n == 4 || n == 8, "device count must be 1, 2, 4 or 8");
     ctx_init(-1);
-    return *g_ctx;
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    DG_REQUIRE(g_ctxs[0]->device == 0, "single-process multi-GPU mode uses devices 0 .. n-1: the primary context must be on device 0");
+    DG_REQUIRE(g_ctxs[0]->world == 1 || (int)g_ctxs.size() == g_ctxs[0]->world, "a multi-process communicator is already active (dg_comm_init)");
+    if ((int)g_ctxs.size() == n) return;
+    DG_REQUIRE(g_ctxs.size() == 1, "the device set cannot be changed once it has been initialised");
+    int count = 0;
+    DG_CUDA(cudaGetDeviceCount(&count));
+    DG_REQUIRE(n <= count, "not enough CUDA devices");
+    Context *me = tl_ctx;
+    for (int d = 1; d < n; d++) g_ctxs.push_back(build_context(d));
+    for (int a = 0; a < n; a++)                          // device-resident inputs on one device are read by the others over NVLink
+        for (int b2 = 0; b2 < n; b2++) {
+            if (a == b2) continue;
+            DG_CUDA(cudaSetDevice(a));
+            cudaError_t e = cudaDeviceEnablePeerAccess(b2, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) DG_CUDA(e);
+            cudaGetLastError();
+        }
+    if (n > 1) comm_init_all(g_ctxs);
+    ctx_bind(me);
+}
+
+void set_func_smem(Context &c, const void *func, size_t bytes) {
+    size_t &have = c.func_smem[func];
+    if (have >= bytes) return;
+    DG_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
 }
 
 const fe *Context::single_table(int log_order) {

@@ -87,11 +87,7 @@ static void launch_pass(Context &c, int log_l, PassGeom g, const fe *src, fe *ds
     int threads = (L * T) >> (log_l < rmax ? log_l : rmax);           // one unit per thread in the largest round
     if (threads > bt) threads = bt;
     if (threads < 32) threads = 32;
-    static std::map<PassKernel, bool> attr_set;
-    if (!attr_set[k]) {
-        DG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set[k] = true;
-    }
+    set_func_smem(c, (const void *)k, 200 * 1024);
     DG_REQUIRE(by <= 65535 && bz <= 65535, "batch too large for one launch");
     k<<<dim3(blocks_x, by, bz), threads, smem, c.stream>>>(src, dst, g); c.launches++;
     DG_CUDA(cudaGetLastError());

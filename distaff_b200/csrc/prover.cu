@@ -305,11 +305,12 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
     const fe program_hash[2] = {last_row[1], last_row[2]};
     fs::ConstraintCoefficients cc = fs::draw_constraint_coefficients(proof->trace_root, ctx_depth, loop_depth, stack_depth, inputs, outputs,
                                                                       op_count, program_hash);
-    static DevBuf d_periodic;
+    DevBuf &d_periodic = c.d_periodic;
     if (!d_periodic.p) {
         std::vector<fe> per = fs::periodic_tables();
         d_periodic.alloc(per.size() * 16, true);
         h2d(c, d_periodic.p, per.data(), per.size() * 16);
+        DG_CUDA(cudaStreamSynchronize(c.stream));
     }
     const size_t T = cc.coefA.size(), nb = cc.bAi.size();
     DevBuf d_coef((2 * T + 4 * nb) * 16), d_violation(4);

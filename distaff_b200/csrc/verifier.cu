@@ -450,7 +450,6 @@ std::string verify_proof(Context &c, const uint8_t program_hash[32], const std::
     for (int j = 0; j < w; j++) { fake[(size_t)j * 128] = P.z1[j]; fake[(size_t)j * 128 + 1] = P.z2[j]; }
     const fe *fake_dev = upload(c, d_fake, fake);
     d_tev.alloc(128 * 16);
-    static DevBuf d_periodic_dummy;
     {
         AirParams A;
         memset(&A, 0, sizeof A);

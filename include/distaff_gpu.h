@@ -33,7 +33,12 @@ extern "C" {
 #define DG_ERR_REJECTED (-6)     /* dg_verify: the proof was rejected; the message is the reference's Err(String) (verifier.rs:28-73) */
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------- */
-int dg_init(int device);                     /* optional; device < 0 = $DG_DEVICE or 0 */
+int dg_init(int device);                     /* optional; device < 0 = $DG_DEVICE or 0; an error if the library already runs on another device */
+/* Single-process multi-GPU: after dg_init_devices(n) (n = 1, 2, 4 or 8; devices 0 .. n-1) ONE call of dg_prove / dg_prove_device from one
+ * host thread shards the proof over the n GPUs -- the library runs one internal host thread and one NCCL communicator per device -- and
+ * returns the same bytes as the single-GPU call.  This is the mode the seam at lib.rs:62 (one synchronous call in one process) needs;
+ * the one-process-per-GPU mode (dg_comm_init below) remains for hosts that already run one rank per GPU. */
+int dg_init_devices(int n_devices);
 const char *dg_last_error(void);             /* thread-local message of the last failing call */
 int dg_device_info(char *name, size_t cap, int *sm_count, size_t *total_mem);
 

@@ -21,3 +21,14 @@ def test_two_rank_proofs_equal_the_oracle():
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "MULTI_GPU_CHECK PASS world 2" in out.stdout
+
+
+def test_single_process_two_devices():
+    """dg_init_devices(2): one process, one dg_prove call per proof, two GPUs (host threads + ncclCommInitAll inside the library)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "single_process_check.py"), "2", "14"], cwd=ROOT, capture_output=True, text=True,
+                         timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "SINGLE_PROCESS_CHECK PASS devices 2" in out.stdout

@@ -13,7 +13,7 @@ hdr, rows = rows[0], rows[1:]
 ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
 # the capture holds warm-up launches, identical proofs and possibly other work after them: one steady-state proof's worth of launches
 # is the window between the last two constraint kernels (stages 4-9 of one proof + stages 1-3 of the next: same kernels, rotated)
-idx = [i for i, r in enumerate(rows) if "constraint_eval_kernel" in r[ki]]
+idx = [i for i, r in enumerate(rows) if "constraint_eval" in r[ki]]
 if len(sys.argv) > 3:
     per_proof = int(sys.argv[3])
     last = rows[-per_proof:]
