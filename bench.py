@@ -225,8 +225,12 @@ def run_ours(args):
     import distaff_b200 as dg
     from distaff_b200 import backend
     info = backend.device_info()
+    single_process = args.single_process and world == 1 and args.gpus > 1
     if world > 1:
         backend.comm_init_from_torch(dist, local_rank)
+    elif single_process:
+        # ONE process, one dg_prove call per proof, args.gpus GPUs: the library runs a host thread + NCCL communicator per device (dg_init_devices)
+        backend.check(backend.lib().dg_init_devices(args.gpus))
 
     tr, name = build_workload(args)
     n, w = tr.length, tr.width
@@ -337,7 +341,7 @@ def run_ours(args):
     peak, peak_kind = peak_gbs()
     L = backend.lib()
     log_n = n.bit_length() - 1
-    cols = min(w, 2)                            # the prover extends the trace two columns per launch (1 GiB of NTT scratch): same shape here
+    cols = min(w, 8)                            # the prover extends the trace eight columns per launch pair (4 GiB of NTT scratch): same shape here
     polys = backend.DeviceBuffer(cols * n * 16).upload(regs[:cols])
     ext = backend.DeviceBuffer(cols * n * 32 * 16)
     ms = ctypes.c_float(0)
@@ -353,16 +357,16 @@ def run_ours(args):
     achieved = alg_bytes / (lde * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:                                        # DRAM bytes per launch from the committed ncu --set full capture of the same launch shape
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))
-        if log_n == 20 and cols == 2:
-            traffic, traffic_src = tj["per_launch_bytes"], "profiles/r01_roofline_traffic.json (ncu dram__bytes_read+write, mean of the two pass launches)"
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_roofline_traffic.json")))
+        if log_n == 20 and cols == tj.get("columns_per_launch"):
+            traffic, traffic_src = tj["per_launch_bytes"], "profiles/r02_roofline_traffic.json (ncu dram__bytes_read+write, mean of the two pass launches)"
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "ntt_pass_kernel (coset LDE x32 of %d trace columns = %d launches)" % (cols, n_pass), "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": alg_bytes / n_pass, "launch_ms": lde / n_pass,
-                "note": "the kernel is integer-ALU bound, not HBM bound: ncu shows the ALU pipe 61-66% busy at 5% DRAM throughput "
-                        "(profiles/r01_ncu_ntt_pass_kernel.txt); 2-pass NTT traffic = write + re-read of the 2^25-point intermediate"}
+                "note": "the kernel is integer-ALU bound, not HBM bound: ncu shows the ALU pipe 59-63% busy with math_pipe_throttle the top stall at 13-16% DRAM "
+                        "throughput (profiles/r02_ncu_ntt_pass_kernel.txt); a 2-pass NTT writes and re-reads the 2^25-point intermediate (floor 3x the algorithmic bytes)"}
     # the bound that actually applies: 128-bit modular arithmetic.  One LDE column = 32 coset NTTs of n points = 32 * (n/2) * log2(n)
     # butterflies (1 modmul + 1 add + 1 sub) + 2 extra modmuls per point (coset factor, inter-pass twiddle), counted as 0.6 butterflies
     bfly = cols * 32.0 * ((n / 2) * log_n + 0.6 * 2 * n)
@@ -398,11 +402,12 @@ def run_ours(args):
         po.set_threads(1)
 
     line = {
-        "metric": metric_name(log_n), "value": value, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(log_n), "value": value, "unit": "ms", "n_gpus": args.gpus if single_process else world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u128 (128-bit prime field) + u32 (blake3)", "data": "synthetic",
         "config": {"workload": workload_name(name, log_n, w),
-                   "parallelism": ("coset-sharded x%d (NCCL all-gather at commitment points)" % world) if world > 1 else "single", "l2": "inputs exceed L2 (trace %d MB, extended trace %d MB)" % (regs.nbytes >> 20, (regs.nbytes * 32) >> 20),
+                   "parallelism": ("coset-sharded x%d, one process per GPU (NCCL all-gather / all-to-all at commitment points)" % world) if world > 1 else
+                                  ("coset-sharded x%d inside ONE process (dg_init_devices: host thread + NCCL communicator per device)" % args.gpus) if single_process else "single", "l2": "inputs exceed L2 (trace %d MB, extended trace %d MB)" % (regs.nbytes >> 20, (regs.nbytes * 32) >> 20),
                    "proof_bytes": len(proof.bytes), "device": info["name"]},
         "stage_ms": [float(x) / args.steps for x in stage_ms],
         "stage_names": STAGE_NAMES,
@@ -550,6 +555,7 @@ def main():
                     help="collatz = the headline 2^20-step workload (default); fibonacci --log-n 16 and merkle --log-n 14 are BASELINE configs 2 and 3")
     ap.add_argument("--ref-log-n", type=int, default=0, help="log2 trace length of the CPU sample (default: chosen to fit the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-process", action="store_true", help="with --gpus N (no torchrun): shard the proof over N GPUs from this one process")
     ap.add_argument("--microbench", action="store_true", help="BASELINE config 5: NTT / LDE / leaf hash / Merkle sweep instead of the proof benchmark")
     ap.add_argument("--quick", action="store_true", help="--microbench: three sizes only")
     ap.add_argument("--verbose", action="store_true")

@@ -89,6 +89,8 @@ static void launch_pass(Context &c, int log_l, PassGeom g, const fe *src, fe *ds
     if (threads < 32) threads = 32;
     set_func_smem(c, (const void *)k, 200 * 1024);
     DG_REQUIRE(by <= 65535 && bz <= 65535, "batch too large for one launch");
+    // (r02: folding the vector index into blockIdx.x so that all columns of a (tile, coset) share the streamed twiddles in L2 cost 120 bytes
+    //  of spills at the 64-register cap and made the trace LDE 1% slower: rejected)
     k<<<dim3(blocks_x, by, bz), threads, smem, c.stream>>>(src, dst, g); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
@@ -251,7 +253,11 @@ void lde_batch(Context &c, const fe *src, fe *dst, int log_n, int log_blowup, in
     const size_t n = (size_t)1 << log_n;
     const unsigned cosets = ncosets ? ncosets : (1u << log_blowup);
     DG_REQUIRE(coset0 + cosets <= (1u << log_blowup), "coset range out of bounds");
-    size_t max_chunk = std::max<size_t>(1, ((size_t)1 << 30) / (n * cosets * sizeof(fe)));
+    // scratch of the two-pass transforms: one intermediate of n * cosets elements per vector; more vectors per launch = fewer passes over
+    // the streamed first-pass twiddles (DG_NTT_SCRATCH_MB, default 4096)
+    static size_t scratch_cap = 0;
+    if (!scratch_cap) { const char *e = getenv("DG_NTT_SCRATCH_MB"); scratch_cap = (size_t)(e ? atoll(e) : 4096) << 20; }
+    size_t max_chunk = std::max<size_t>(1, scratch_cap / (n * cosets * sizeof(fe)));
     if (max_chunk > 65535) max_chunk = 65535;
     for (size_t b0 = 0; b0 < (size_t)batch; b0 += max_chunk) {
         size_t nb = std::min(max_chunk, (size_t)batch - b0);

@@ -254,7 +254,7 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
             ntt_batch(c, d_regs, polys.as<fe>(), log_n, w, n, n, true);
             lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
         } else {
-            const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>(w, ((uint64_t)1 << 25) / (n * 16)));   // ~32 MB per upload
+            const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>(w, ((uint64_t)1 << 26) / (n * 16)));   // ~64 MB per upload
             TraceUploader up(c, d_regs, host_cols, w, n, chunk);
             for (int i = 0; i < up.chunks(); i++) {
                 const int j0 = i * chunk, cols = std::min(w, j0 + chunk) - j0;

@@ -1,5 +1,14 @@
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -40 ) > gpurun_out/c6_pytest.log 2>&1
-cat gpurun_out/c6_pytest.log
-( timeout 600 python bench.py --microbench --verbose 2> gpurun_out/c6_micro_verbose.log | tail -1 ) > gpurun_out/c6_microbench_n1.json
-cat gpurun_out/c6_micro_verbose.log | tail -40
+export BENCH_NO_SMI=1
+run() { ( env "$@" timeout 300 python tools/variant_bench.py 20 3 2>&1 | grep -E "VARIANT|Error|error" | tail -2 ) >> gpurun_out/c9_variants.log 2>&1; }
+: > gpurun_out/c9_variants.log
+run DG_X=default
+run DG_NTT_ZFAST=0
+run DG_NTT_SCRATCH_MB=1024
+run DG_NTT_SCRATCH_MB=1024 DG_NTT_ZFAST=0
+run DG_NTT_SCRATCH_MB=14000
+cat gpurun_out/c9_variants.log
+unset BENCH_NO_SMI
+bash tools/capture_profiles.sh r02b 20
+( timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -1 ) > gpurun_out/c9_bench1.json
+cut -c1-700 gpurun_out/c9_bench1.json

@@ -12,10 +12,10 @@ capture() {  # name regex skip count
     ncu -i $tmp/$1.ncu-rep --page source --csv 2>/dev/null | gzip -9 > $out/${tag}_$1_source.csv.gz
     ncu -i $tmp/$1.ncu-rep --page details 2>/dev/null | head -400 > $out/${tag}_$1_details.txt
 }
-# one proof launches 34 ntt_pass_kernel (2 interpolation + 13 x 2 trace LDE + 2 + 2 + 2): skip the first proof and the interpolation of the
+# one proof launches 16 ntt_pass_kernel (2 interpolation + 4 x 2 trace LDE + 2 + 2 + 2): skip the first proof and the interpolation of the
 # second, capture one (strided pass, contiguous pass) pair of the trace LDE
-capture ntt ntt_pass_kernel 40 2
+capture ntt ntt_pass_kernel 18 2
 capture air constraint_eval 1 1
-capture hash hash_rows_kernel 1 1
+capture hash "^hash_rows_kernel" 1 1
 capture merkle merkle_level 20 1
 du -sh $out
