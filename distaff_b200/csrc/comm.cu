@@ -100,12 +100,13 @@ void comm_finalize(Context &c) {
 }
 
 // recv = concatenation over ranks of each rank's `bytes` bytes (rank-major); with one rank it is a device copy
-void comm_all_gather(Context &c, const void *send, void *recv, size_t bytes) {
+void comm_all_gather(Context &c, const void *send, void *recv, size_t bytes, cudaStream_t stream) {
+    if (!stream) stream = c.stream;
     if (c.world == 1) {
-        if (send != recv) DG_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, c.stream));
+        if (send != recv) DG_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, stream));
         return;
     }
-    nccl_check(g_nccl.AllGather(send, recv, bytes, /*ncclUint8*/ 1, (ncclComm_t)c.nccl_comm, c.stream), "ncclAllGather");
+    nccl_check(g_nccl.AllGather(send, recv, bytes, /*ncclUint8*/ 1, (ncclComm_t)c.nccl_comm, stream), "ncclAllGather");
 }
 
 // recv[g] (bytes each) = the chunk rank g sent to this rank; send[h] = the chunk for rank h.  One grouped send/recv per peer.
@@ -120,6 +121,15 @@ void comm_all_to_all(Context &c, const void *send, void *recv, size_t bytes) {
         nccl_check(g_nccl.Recv((uint8_t *)recv + (size_t)p * bytes, bytes, /*ncclUint8*/ 1, p, (ncclComm_t)c.nccl_comm, c.stream), "ncclRecv");
     }
     nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
+}
+
+// recv = element-wise sum over the ranks of `count` uint32 values
+void comm_all_reduce_sum_u32(Context &c, const unsigned *send, unsigned *recv, size_t count) {
+    if (c.world == 1) {
+        if (send != recv) DG_CUDA(cudaMemcpyAsync(recv, send, count * 4, cudaMemcpyDeviceToDevice, c.stream));
+        return;
+    }
+    nccl_check(g_nccl.AllReduce(send, recv, count, /*ncclUint32*/ 3, /*ncclSum*/ 0, (ncclComm_t)c.nccl_comm, c.stream), "ncclAllReduce");
 }
 
 // in-place max over ranks of `count` uint32 values

@@ -118,6 +118,7 @@ struct Context {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;     // host->device uploads that overlap compute (prover.cu stage 1)
+    cudaStream_t comm_stream = nullptr;     // collectives that overlap compute (the all-gather of the trace polynomials)
     std::mutex mu;
     // small root tables for the in-shared-memory transforms: roots[inv][l] = w_{2^l}^m, m < 2^(l-1), l = 1..MAX_LOG_L
     DevBuf small_roots[2];
@@ -180,8 +181,9 @@ void comm_unique_id(uint8_t out[128]);
 void comm_init(Context &c, int rank, int world, const uint8_t id_bytes[128]);
 void comm_init_all(std::vector<Context *> &ctxs);     // single process: ncclCommInitAll over the contexts' devices
 void comm_finalize(Context &c);
-void comm_all_gather(Context &c, const void *send, void *recv, size_t bytes_per_rank);
+void comm_all_gather(Context &c, const void *send, void *recv, size_t bytes_per_rank, cudaStream_t stream = nullptr);   // default: the compute stream
 void comm_all_to_all(Context &c, const void *send, void *recv, size_t bytes_per_peer);
 void comm_all_reduce_max_u32(Context &c, unsigned *buf, size_t count);
+void comm_all_reduce_sum_u32(Context &c, const unsigned *send, unsigned *recv, size_t count);
 
 }  // namespace dg

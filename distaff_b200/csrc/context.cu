@@ -72,6 +72,7 @@ static Context *build_context(int device) {
     c->num_sms = prop.multiProcessorCount;
     DG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     DG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    DG_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
     {   // keep freed blocks in the pool instead of returning them to the driver between proofs
         cudaMemPool_t pool;
         DG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));

@@ -275,9 +275,24 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
             }
         }
     sub.mark("1.intt");
-        comm_all_gather(c, polys.as<fe>() + (size_t)g * cpr * n, polys.p, (size_t)cpr * n * 16);       // in place
-    sub.mark("1.gather_polys");
-        lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
+        // the all-gather of the polynomials runs on the communication stream while this rank already extends its own columns
+        cudaEvent_t ev_own, ev_all;
+        DG_CUDA(cudaEventCreateWithFlags(&ev_own, cudaEventDisableTiming));
+        DG_CUDA(cudaEventCreateWithFlags(&ev_all, cudaEventDisableTiming));
+        DG_CUDA(cudaEventRecord(ev_own, c.stream));
+        DG_CUDA(cudaStreamWaitEvent(c.comm_stream, ev_own, 0));
+        comm_all_gather(c, polys.as<fe>() + (size_t)g * cpr * n, polys.p, (size_t)cpr * n * 16, c.comm_stream);       // in place
+        DG_CUDA(cudaEventRecord(ev_all, c.comm_stream));
+        if (mine > 0)
+            lde_batch(c, polys.as<fe>() + (size_t)j0 * n, ext.as<fe>() + (size_t)j0 * N_loc, log_n, log_b, 1, mine, n, N_loc, c0, (unsigned)nc);
+    sub.mark("1.lde_own");
+        DG_CUDA(cudaStreamWaitEvent(c.stream, ev_all, 0));
+        if (j0 > 0) lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, j0, n, N_loc, c0, (unsigned)nc);
+        if (j0 + mine < w)
+            lde_batch(c, polys.as<fe>() + (size_t)(j0 + mine) * n, ext.as<fe>() + (size_t)(j0 + mine) * N_loc, log_n, log_b, 1, w - j0 - mine, n, N_loc, c0,
+                      (unsigned)nc);
+        cudaEventDestroy(ev_own);
+        cudaEventDestroy(ev_all);
     }
 
     // ---- 2: trace Merkle tree ----------------------------------------------------------------------------------------------------------
@@ -472,7 +487,9 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         for (;;) {
             const int log_r = lay.log_d - 2;
             const uint64_t R = 1ULL << log_r;
-            if (local && log_r - log_b < 6) {                  // small layer: gather it once and finish redundantly on every rank
+            // layers below 2^22 values are latency-bound (two collectives per sharded tree cost more than hashing them whole): gather the
+            // first such layer once (<= 32 MB) and finish redundantly on every rank
+            if (local && (lay.log_d < 22 || log_r - log_b < 6)) {
                 fri_gathered.alloc((size_t)16 << lay.log_d);
                 comm_all_gather(c, cur, fri_gathered.p, ((size_t)16 << lay.log_d) >> log_g);     // rank-major == coset-major
                 cur = fri_gathered.as<fe>();

@@ -158,6 +158,12 @@ __global__ void fetch_units_kernel(const unsigned long long *__restrict__ req, u
     out[t] = base ? base[req[2 * t + 1]] : make_uint4(0, 0, 0, 0);
 }
 
+// replicated units are identical on every rank: all ranks but rank 0 zero theirs so that the sum over the ranks returns the value once
+__global__ void zero_replicated_kernel(uint4 *__restrict__ out, const unsigned char *__restrict__ replicated, unsigned count, int zero_them) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count && replicated[t] && zero_them) out[t] = make_uint4(0, 0, 0, 0);
+}
+
 void FetchBatch::run() {
     const size_t n = owner_.size();
     out_.assign(n * 16, 0);
@@ -171,15 +177,23 @@ void FetchBatch::run() {
         DG_CUDA(cudaStreamSynchronize(c_.stream));
         return;
     }
-    DevBuf all(n * 16 * c_.world);
-    comm_all_gather(c_, d_out.p, all.p, n * 16);
-    std::vector<uint8_t> host(n * 16 * c_.world);
-    DG_CUDA(cudaMemcpyAsync(host.data(), all.p, host.size(), cudaMemcpyDeviceToHost, c_.stream));
-    DG_CUDA(cudaStreamSynchronize(c_.stream));
-    for (size_t t = 0; t < n; t++) {
-        const int o = owner_[t] < 0 ? c_.rank : owner_[t];
-        memcpy(out_.data() + t * 16, host.data() + ((size_t)o * n + t) * 16, 16);
+    // exactly one rank contributes each owned unit (the others wrote zeros), so a 32-bit integer sum over the ranks assembles the
+    // result bit for bit; replicated units (owner < 0) were read by every rank: keep the local copy of those
+    DevBuf summed(n * 16);
+    std::vector<unsigned char> keep(n);
+    bool any_replicated = false;
+    for (size_t t = 0; t < n; t++) { keep[t] = owner_[t] < 0; any_replicated |= owner_[t] < 0; }
+    if (any_replicated) {
+        DevBuf d_keep(n);
+        DG_CUDA(cudaMemcpyAsync(d_keep.p, keep.data(), n, cudaMemcpyHostToDevice, c_.stream));
+        zero_replicated_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c_.stream>>>(d_out.as<uint4>(), d_keep.as<unsigned char>(), (unsigned)n, c_.rank != 0); c_.launches++;
+        DG_CUDA(cudaGetLastError());
+        comm_all_reduce_sum_u32(c_, d_out.as<unsigned>(), summed.as<unsigned>(), n * 4);
+    } else {
+        comm_all_reduce_sum_u32(c_, d_out.as<unsigned>(), summed.as<unsigned>(), n * 4);
     }
+    DG_CUDA(cudaMemcpyAsync(out_.data(), summed.p, n * 16, cudaMemcpyDeviceToHost, c_.stream));
+    DG_CUDA(cudaStreamSynchronize(c_.stream));
 }
 
 }  // namespace dg
