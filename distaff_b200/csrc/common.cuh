@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -118,6 +119,7 @@ struct Context {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;     // host->device uploads that overlap compute (prover.cu stage 1)
+    std::function<void(const char *)> mark;     // optional sub-stage marker of the running proof (DG_SUBSTAGE), else empty
     cudaStream_t comm_stream = nullptr;     // collectives that overlap compute (the all-gather of the trace polynomials)
     std::mutex mu;
     // small root tables for the in-shared-memory transforms: roots[inv][l] = w_{2^l}^m, m < 2^(l-1), l = 1..MAX_LOG_L

@@ -49,7 +49,7 @@ struct SubClock {
             snprintf(buf, sizeof buf, " %s=%.3f", marks[i].first.c_str(), ms);
             line += buf;
         }
-        if (rank == 0) fprintf(stderr, "%s\n", line.c_str());
+        if (rank == 0 || atoi(getenv("DG_SUBSTAGE")) >= 2) fprintf(stderr, "%s\n", line.c_str());
         for (auto &m : marks) cudaEventDestroy(m.second);
         marks.clear();
     }
@@ -229,6 +229,8 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
     ArenaScope arena_scope;                   // all DevBufs below come from the per-proof arena (no driver allocation inside a proof)
     StageClock clk(c.stream);
     SubClock sub(c.stream);
+    if (sub.on) c.mark = [&sub](const char *name) { sub.mark(name); }; else c.mark = nullptr;
+    struct MarkReset { Context &c; ~MarkReset() { c.mark = nullptr; } } mark_reset{c};
     const unsigned long long launches0 = c.launches;
     Proof *proof = new Proof();
     std::unique_ptr<Proof> guard(proof);
@@ -245,10 +247,14 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
     // ---- 1: extend execution trace ---------------------------------------------------------------------------------------------------
     clk.mark(0);
     sub.mark("start");
-    // G > 1: the interpolation is sharded by columns (rank g interpolates columns [g cpr, (g + 1) cpr) and only needs -- and, from a
-    // host trace, only uploads -- those registers), the polynomials are all-gathered, and every rank extends all columns on its cosets
-    const int cpr = (w + G - 1) / G;                           // columns per rank (the last rank may own fewer, or none)
-    DevBuf polys((size_t)cpr * G * n * 16), ext((size_t)w * N_loc * 16);
+    // G > 1: the interpolation is sharded by columns -- rank r interpolates the columns [col_start(r), col_start(r) + col_count(r)), an
+    // even split (the first w mod G ranks own one more), and only needs (from a host trace: only uploads) those registers -- the
+    // polynomials are all-gathered (equal slots of cpr columns per rank, then compacted into natural column order) and every rank
+    // extends all columns on its cosets
+    const int cpr = (w + G - 1) / G;                           // slot size of the gather = largest share
+    auto col_count = [&](int r) { return w / G + (r < w % G ? 1 : 0); };
+    auto col_start = [&](int r) { return r * (w / G) + std::min(r, w % G); };
+    DevBuf polys((size_t)w * n * 16), ext((size_t)w * N_loc * 16);
     if (G == 1) {
         if (!host_cols) {
             ntt_batch(c, d_regs, polys.as<fe>(), log_n, w, n, n, true);
@@ -264,27 +270,32 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
             }
         }
     } else {
-        const int j0 = std::min(w, g * cpr), mine = std::min(w, j0 + cpr) - j0;
+        const int j0 = col_start(g), mine = col_count(g);
+        DevBuf own((size_t)cpr * n * 16), slots((size_t)cpr * G * n * 16);
         if (mine > 0) {
             if (host_cols) {
                 TraceUploader up(c, d_regs + (size_t)j0 * n, host_cols + j0, mine, n, 1);      // one column per chunk: all staging workers busy
                 for (int i = 0; i < up.chunks(); i++) up.wait_chunk(i);
-                ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, mine, n, n, true);
+                ntt_batch(c, d_regs + (size_t)j0 * n, own.as<fe>(), log_n, mine, n, n, true);
             } else {
-                ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, mine, n, n, true);
+                ntt_batch(c, d_regs + (size_t)j0 * n, own.as<fe>(), log_n, mine, n, n, true);
             }
         }
     sub.mark("1.intt");
-        // the all-gather of the polynomials runs on the communication stream while this rank already extends its own columns
+        // the all-gather of the polynomials (and their compaction into column order) runs on the communication stream while this rank
+        // already extends its own columns
         cudaEvent_t ev_own, ev_all;
         DG_CUDA(cudaEventCreateWithFlags(&ev_own, cudaEventDisableTiming));
         DG_CUDA(cudaEventCreateWithFlags(&ev_all, cudaEventDisableTiming));
         DG_CUDA(cudaEventRecord(ev_own, c.stream));
         DG_CUDA(cudaStreamWaitEvent(c.comm_stream, ev_own, 0));
-        comm_all_gather(c, polys.as<fe>() + (size_t)g * cpr * n, polys.p, (size_t)cpr * n * 16, c.comm_stream);       // in place
+        comm_all_gather(c, own.p, slots.p, (size_t)cpr * n * 16, c.comm_stream);
+        for (int r = 0; r < G; r++)
+            if (col_count(r) > 0)
+                DG_CUDA(cudaMemcpyAsync(polys.as<fe>() + (size_t)col_start(r) * n, slots.as<fe>() + (size_t)r * cpr * n, (size_t)col_count(r) * n * 16,
+                                        cudaMemcpyDeviceToDevice, c.comm_stream));
         DG_CUDA(cudaEventRecord(ev_all, c.comm_stream));
-        if (mine > 0)
-            lde_batch(c, polys.as<fe>() + (size_t)j0 * n, ext.as<fe>() + (size_t)j0 * N_loc, log_n, log_b, 1, mine, n, N_loc, c0, (unsigned)nc);
+        if (mine > 0) lde_batch(c, own.as<fe>(), ext.as<fe>() + (size_t)j0 * N_loc, log_n, log_b, 1, mine, n, N_loc, c0, (unsigned)nc);
     sub.mark("1.lde_own");
         DG_CUDA(cudaStreamWaitEvent(c.stream, ev_all, 0));
         if (j0 > 0) lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, j0, n, N_loc, c0, (unsigned)nc);
@@ -420,17 +431,24 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
     {
         PowTable z_t(c, z, E + 1), zi_t(c, host_inv(z), E + 1), zg_t(c, zg, n + 1), zgi_t(c, host_inv(zg), n + 1);
         TwiddleRef g_t = c.twiddle(log_n, false);
-        // trace polynomials at z and z*g: every rank evaluates its own columns (the split of stage 1), the 2 cpr values per rank are gathered
+        // trace polynomials at z and z*g: every rank evaluates its own columns (the split of stage 1); slots of 2 cpr values are gathered
         const int wp = cpr * G;
         DevBuf d_deep((size_t)(2 * wp + 2) * 16);
+        DG_CUDA(cudaMemsetAsync(d_deep.p, 0, d_deep.bytes, c.stream));
         {
-            const int j0 = std::min(w, g * cpr), mine = std::min(w, j0 + cpr) - j0;
-            if (mine > 0) eval_polys_at(c, polys.as<fe>() + (size_t)j0 * n, n, mine, z_t.ref(), g_t, true, d_deep.as<fe>() + 2 * j0);
+            const int j0 = col_start(g), mine = col_count(g);
+            if (mine > 0) eval_polys_at(c, polys.as<fe>() + (size_t)j0 * n, n, mine, z_t.ref(), g_t, true, d_deep.as<fe>() + (size_t)2 * g * cpr);
             if (G > 1) comm_all_gather(c, d_deep.as<fe>() + (size_t)2 * g * cpr, d_deep.p, (size_t)2 * cpr * 16);
         }
         eval_polys_at(c, combined.as<fe>(), E, 1, z_t.ref(), g_t, false, d_deep.as<fe>() + 2 * wp);
-        std::vector<fe> deep(2 * wp + 2);
-        d2h(c, deep.data(), d_deep.p, deep.size() * 16);
+        std::vector<fe> deep_slots(2 * wp + 2), deep(2 * w + 2);
+        d2h(c, deep_slots.data(), d_deep.p, deep_slots.size() * 16);
+        for (int r = 0; r < G; r++)
+            for (int o = 0; o < col_count(r); o++) {
+                deep[2 * (col_start(r) + o)] = deep_slots[2 * (r * cpr + o)];
+                deep[2 * (col_start(r) + o) + 1] = deep_slots[2 * (r * cpr + o) + 1];
+            }
+        deep[2 * w] = deep_slots[2 * wp];
     sub.mark("6.deep_values");
         fe sub1 = fe_make(0, 0), sub2 = fe_make(0, 0);
         for (int i = 0; i < w; i++) {
@@ -438,7 +456,7 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
             sub1 = fe_add(sub1, fe_mul(state1[i], dc.trace1[i]));
             sub2 = fe_add(sub2, fe_mul(state2[i], dc.trace2[i]));
         }
-        const fe c_at_z = deep[2 * wp];
+        const fe c_at_z = deep[2 * w];
         DevBuf d_cc((size_t)2 * w * 16), t12(2 * n * 16);
         h2d(c, d_cc.p, dc.trace1.data(), (size_t)w * 16);
         h2d(c, d_cc.as<fe>() + w, dc.trace2.data(), (size_t)w * 16);

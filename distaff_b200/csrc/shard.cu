@@ -135,13 +135,16 @@ void ShardedTree::build(Context &c, const void *items_local_dev, uint64_t n, int
         // re-shard the roots by k-range: recv[g'][k'] = root (k = g n/G + k') of rank g'
         const uint64_t chunk = n / G;
         DevBuf recv(n * 32);
+        if (c.mark) c.mark("tree.local");
         comm_all_to_all(c, roots, recv.p, chunk * 32);
+        if (c.mark) c.mark("tree.a2a");
         mid.alloc(2 * n * 32);
         interleave_roots(c, recv.p, mid.p, chunk, log_g);           // mid[n + k' G + g'] : nodes [g n, (g + 1) n) of the global level n G
         merkle_finish(c, mid.p, n);                                 // mid[1] = global node G + g
         top.alloc(2 * G * 32);
         comm_all_gather(c, (const uint8_t *)mid.p + 32, (uint8_t *)top.p + G * 32, 32);
         merkle_finish(c, top.p, G);
+        if (c.mark) c.mark("tree.mid+top");
         mid_p = mid.p; top_p = top.p;
     }
     if (fetch_root) {

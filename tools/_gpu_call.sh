@@ -1,14 +1,7 @@
 mkdir -p gpurun_out
-export BENCH_NO_SMI=1
-run() { ( env "$@" timeout 300 python tools/variant_bench.py 20 3 2>&1 | grep -E "VARIANT|Error|error" | tail -2 ) >> gpurun_out/c9_variants.log 2>&1; }
-: > gpurun_out/c9_variants.log
-run DG_X=default
-run DG_NTT_ZFAST=0
-run DG_NTT_SCRATCH_MB=1024
-run DG_NTT_SCRATCH_MB=1024 DG_NTT_ZFAST=0
-run DG_NTT_SCRATCH_MB=14000
-cat gpurun_out/c9_variants.log
-unset BENCH_NO_SMI
-bash tools/capture_profiles.sh r02b 20
-( timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -1 ) > gpurun_out/c9_bench1.json
-cut -c1-700 gpurun_out/c9_bench1.json
+( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29546 tools/multi_gpu_check.py 2>&1 | grep -E "MULTI_GPU_CHECK|identical=False|rror" | tail -5 ) > gpurun_out/c12_check4.log 2>&1
+cat gpurun_out/c12_check4.log
+( DG_SUBSTAGE=1 BENCH_NO_SMI=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 4 --steps 3 --warmup 2 --no-cpu-baseline 2>&1 | grep -E "^\{|SUBSTAGE|rror" | cut -c1-700 | tail -3 ) > gpurun_out/c12_bench4.log 2>&1
+cat gpurun_out/c12_bench4.log
+( timeout 600 python tools/single_process_check.py 4 14 2>&1 | tail -3 ) > gpurun_out/c12_single4.log 2>&1
+cat gpurun_out/c12_single4.log
