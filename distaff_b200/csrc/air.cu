@@ -956,16 +956,12 @@ void launch_constraint_eval(Context &c, const AirParams &P) {
     const unsigned long long n = 1ULL << P.log_n;
     // the shared-memory variants need whole blocks inside one coset and at most ~200 KB of rows per block
     if (v >= 5 && (n < 128 || (size_t)P.w * 129 * sizeof(fe) > 200 * 1024)) v = 1;
-    // B200, 2^20 steps x 26 registers: per-thread arrays (r01) (128, 4) 20.9 ms, (256, 2) 22.3, (256, 1) 28.1;
+    // B200, 2^20 steps x 26 registers: per-thread arrays (r01) (128 threads, 4 blocks/SM) 20.9 ms, (256, 2) 22.3, (256, 1) 28.1;
     // shared-memory rows (r02): stack-like columns only (128, 4) 19.9 / (128, 3) 21.3; all columns (128, 4) 19.1 / (128, 3) 20.6
     switch (v) {
-        case 2: DG_AIR_LAUNCH(256, 2); break;
-        case 4: DG_AIR_LAUNCH(256, 1); break;
-        case 5: DG_AIR_LAUNCH_SMEM(128, 4, false); break;
-        case 6: DG_AIR_LAUNCH_SMEM(128, 4, true); break;
-        case 7: DG_AIR_LAUNCH_SMEM(128, 3, false); break;
-        case 8: DG_AIR_LAUNCH_SMEM(128, 3, true); break;
-        default: DG_AIR_LAUNCH(128, 4); break;
+        case 5: DG_AIR_LAUNCH_SMEM(128, 4, false); break;      // only the context / loop / stack columns staged
+        case 6: DG_AIR_LAUNCH_SMEM(128, 4, true); break;       // default
+        default: DG_AIR_LAUNCH(128, 4); break;                 // per-thread arrays: short traces (n < 128) and very wide ones
     }
     c.launches++;
     DG_CUDA(cudaGetLastError());

@@ -244,6 +244,7 @@ int dg_ntt(uint8_t *values, uint32_t log_n, uint32_t batch, int inverse) {
     return guarded([&] {
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(values, "null buffer");
         DG_REQUIRE(log_n >= 1 && log_n <= 30 && batch >= 1, "invalid transform size");
         const size_t bytes = ((size_t)16 << log_n) * batch;
         DevBuf d(bytes);
@@ -257,6 +258,7 @@ int dg_lde(const uint8_t *values, uint8_t *extended, uint32_t log_n, uint32_t lo
     return guarded([&] {
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(values && extended, "null buffer");
         DG_REQUIRE(log_n >= 1 && log_blowup >= 1 && log_n + log_blowup <= 30 && batch >= 1 && batch <= 65535, "invalid extension size");
         const size_t n = (size_t)1 << log_n, N = n << log_blowup;
         DevBuf d_in(n * batch * 16), d_ext(N * batch * 16), d_out(N * batch * 16);
@@ -273,6 +275,7 @@ int dg_merkle_build(const uint8_t *leaves, uint64_t n_leaves, uint8_t *nodes) {
     return guarded([&] {
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(leaves && nodes, "null buffer");
         DG_REQUIRE(n_leaves >= 2 && (n_leaves & (n_leaves - 1)) == 0, "number of leaves must be a power of 2 and >= 2");
         DevBuf d_l(n_leaves * 32), d_n(n_leaves * 32);
         DG_CUDA(cudaMemcpyAsync(d_l.p, leaves, n_leaves * 32, cudaMemcpyHostToDevice, c.stream));
@@ -311,6 +314,7 @@ int dg_hash_rows(const uint8_t *columns, uint32_t width, uint64_t rows, uint8_t 
     return guarded([&] {
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(columns && digests, "null buffer");
         DG_REQUIRE(width >= 1 && width < 128 && rows >= 1, "invalid matrix shape");
         DevBuf d_c((size_t)width * rows * 16), d_d(rows * 32);
         DG_CUDA(cudaMemcpyAsync(d_c.p, columns, (size_t)width * rows * 16, cudaMemcpyHostToDevice, c.stream));
@@ -324,6 +328,7 @@ int dg_find_pow_nonce(const uint8_t seed[32], uint32_t grinding_factor, uint64_t
     return guarded([&] {
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(seed && nonce, "null argument");
         DG_REQUIRE(grinding_factor <= 32, "grinding factor cannot be greater than 32");
         unsigned long long n = pow_search(c, seed, grinding_factor);
         *nonce = n;
@@ -334,6 +339,8 @@ int dg_field_op(int op, int impl, const uint8_t *a, const uint8_t *b, uint8_t *o
     return guarded([&] {
         Context &c = ctx();
         std::lock_guard<std::mutex> lk(c.mu);
+        DG_REQUIRE(a && out && n >= 1 && op >= 0 && op <= 5, "invalid argument");
+        DG_REQUIRE(b || op == 3, "second operand missing");
         DevBuf da(n * 16), db(n * 16), dout(n * 16);
         DG_CUDA(cudaMemcpyAsync(da.p, a, n * 16, cudaMemcpyHostToDevice, c.stream));
         if (b) DG_CUDA(cudaMemcpyAsync(db.p, b, n * 16, cudaMemcpyHostToDevice, c.stream));
@@ -442,7 +449,7 @@ int dg_host_shard_locate(uint64_t n, int log_blk, int log_g, int is_node, uint64
 
 // ---- host-only helpers (no device access) ---------------------------------------------------------------------------------------------
 int dg_host_prng_vector(const uint8_t seed[32], uint64_t count, uint8_t *out16) {
-    return guarded([&] { std::vector<fe> v = fs::prng_vector(seed, count); memcpy(out16, v.data(), count * 16); });
+    return guarded([&] { DG_REQUIRE(seed && (out16 || count == 0), "null argument"); std::vector<fe> v = fs::prng_vector(seed, count); memcpy(out16, v.data(), count * 16); });
 }
 int dg_host_query_positions(const uint8_t seed[32], uint64_t domain_size, uint32_t extension_factor, uint32_t num_queries, uint64_t *out) {
     return guarded([&] {
@@ -455,6 +462,9 @@ int dg_host_query_positions(const uint8_t seed[32], uint64_t domain_size, uint32
 int dg_host_blake3(const uint8_t *data, size_t len, uint8_t out32[32]) { return guarded([&] { fs::blake3_short(data, len, out32); }); }
 int dg_host_plan_batch(const uint64_t *indexes, uint32_t n_indexes, uint64_t n_leaves, uint64_t *out, size_t cap, size_t *written) {
     return guarded([&] {
+        DG_REQUIRE(indexes && out && written, "null argument");
+        DG_REQUIRE(n_leaves >= 2 && (n_leaves & (n_leaves - 1)) == 0, "number of leaves must be a power of 2 and >= 2");
+        for (uint32_t i = 0; i < n_indexes; i++) DG_REQUIRE(indexes[i] < n_leaves, "invalid index (merkle.rs:296-303 asserts index <= max_valid)");
         fs::BatchPlan plan = fs::plan_batch_proof(std::vector<uint64_t>(indexes, indexes + n_indexes), n_leaves);
         std::vector<uint64_t> flat = {(uint64_t)plan.nodes.size(), (uint64_t)plan.depth};
         for (auto &slot : plan.nodes) {

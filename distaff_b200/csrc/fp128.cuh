@@ -6,7 +6,7 @@
 // The reference reduces with two 128x64 partial products (field.rs:38-73); here the full 256-bit product is formed with
 // 32-bit multiply-add chains (IMAD) and folded twice through C (Solinas-style), which maps onto the integer pipes of
 // the SM without any division.  Results are the canonical representatives, so every value is bit-identical to the
-// reference's `field::{add,sub,mul}` (checked against the oracle in tests/test_gpu_field.py).
+// reference's `field::{add,sub,mul}` (checked against the oracle and Python integers in tests/test_gpu_blocks.py).
 #pragma once
 #include <cstdint>
 
@@ -27,7 +27,7 @@ __host__ __device__ __forceinline__ bool fe_eq(fe a, fe b) { return a.lo == b.lo
 
 // ---------------------------------------------------------------------------------------------------------------------
 // portable restatement of the same folding (plain C++): the host path (table setup, unit tests of the logic on the CPU
-// box) and the cross-check for the PTX path in tests/test_gpu_field.py
+// box) and the cross-check for the PTX path in tests/test_gpu_blocks.py
 // ---------------------------------------------------------------------------------------------------------------------
 namespace portable {
 

@@ -211,3 +211,31 @@ def test_crafted_multiplication_operands_are_what_they_claim():
             small += 1
     assert small == len(pairs)
     assert g.pairs() == pairs                                   # deterministic
+
+
+def test_generator_against_the_published_chacha20_vector(L):
+    """External pin (no code of this repo involved in the expected values): the ChaCha20 keystream for the all-zero key and nonce is
+    the published test vector 76b8e0ad a0f13d90 405d6ae5 5386bd28 bdd219b8 a08ded1a a836efcc 8b770dc7 ...  StdRng::from_seed([0; 32])
+    (rand 0.7.3 = rand_chacha ChaCha20, 64-bit counter 0, stream 0) emits those bytes; next_u64 = two words, low first;
+    Uniform(0..2^32) for usize = the top 32 bits of a u64; compute_query_positions drops multiples of the extension factor
+    (stark/utils/mod.rs:25-44).  So the first draw 0x903df1a0 (a multiple of 32) is rejected and the positions start with 0x28bd8653."""
+    import ctypes
+    ks = bytes.fromhex("76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586")
+    words = [int.from_bytes(ks[4 * i:4 * i + 4], "little") for i in range(16)]
+    u64s = [words[2 * i] | (words[2 * i + 1] << 32) for i in range(8)]
+    expect = []
+    for v in u64s:
+        p = v >> 32                                   # Uniform(0..2^32): widening multiply by 2^32 = top 32 bits, zone = all
+        if p % 32 != 0 and p not in expect:
+            expect.append(p)
+    assert expect[0] == 0x28bd8653 and (u64s[0] >> 32) == 0x903df1a0
+    out = (ctypes.c_uint64 * 5)()
+    assert L.dg_host_query_positions(bytes(32), 1 << 32, 32, 5, out) == 0
+    assert list(out) == expect[:5]
+    # and field::prng_vector's first element for the zero seed: floor(v * M / 2^128) with v = u64s[0] | u64s[1] << 64 (Standard u128: low word first)
+    M = 2**128 - 45 * 2**40 + 1
+    v = u64s[0] | (u64s[1] << 64)
+    assert (v * M) % 2**128 <= M - 1                  # accepted on the first draw
+    buf = (ctypes.c_uint8 * 16)()
+    assert L.dg_host_prng_vector(bytes(32), 1, buf) == 0
+    assert int.from_bytes(bytes(buf), "little") == (v * M) >> 128
