@@ -27,7 +27,7 @@ def dg():
 @pytest.fixture(scope="module")
 def fast_oracle(po):
     """the oracle with all host threads (identical bytes for any thread count: tests/test_oracle_stark.py::test_threads_do_not_change_the_proof)"""
-    po.set_threads(os.cpu_count() or 1)
+    po.set_threads(min(32, os.cpu_count() or 1))      # the restatement is fastest at ~32 threads on the 128-thread hosts (profiles/r02_oracle_threads.txt)
     yield po
     po.set_threads(1)
 
