@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_kernel(cons
 // of in per-thread arrays, which the runtime loop bounds used to force into local memory (r01: 1585 STL / 1196 LDL, 6.5 GB of DRAM
 // writes per 2^20-step proof); stack slots >= 8 are folded into the accumulators as soon as they are evaluated.
 // STAGE_DEC: the 15 decoder registers are staged as well (read from shared memory at every use) instead of being held in registers.
-template <int BLOCK, int MIN_BLOCKS, bool STAGE_DEC>
+template <int BLOCK, int MIN_BLOCKS, bool STAGE_DEC, bool WIDE_SLOTS>
 __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_smem_kernel(const AirParams P) {
     extern __shared__ __align__(16) unsigned char air_smem[];
     fe *s_rows = reinterpret_cast<fe *>(air_smem);
@@ -775,6 +775,19 @@ __global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) constraint_eval_smem_kernel
         // generic part of slot i; fc / fl1 / fl2 / fl4 are the copy and left-shift flag sums that apply to this slot
         auto slot_value = [&](const int i, const fe fc, const fe fl1, const fe fl2, const fe fl4) -> fe {
             const fe nwi = NW(i);
+            if (WIDE_SLOTS) {
+                // the seven products of a slot are accumulated unreduced (288 bits) and reduced once: 7 x (product + 9-limb add) + 1 reduction
+                // instead of 7 x (modular product + modular add)
+                fe_wide acc7;
+                wide_set(acc7, DG_MUL_WIDE(fc, fe_sub(O(i), nwi)));
+                if (i >= 1) wide_add(acc7, DG_MUL_WIDE(f_rs1, fe_sub(O(i - 1), nwi)));
+                if (i >= 2) wide_add(acc7, DG_MUL_WIDE(f_rs2, fe_sub(O(i - 2), nwi)));
+                if (i >= 4) wide_add(acc7, DG_MUL_WIDE(f_rs4, fe_sub(O(i - 4), nwi)));
+                wide_add(acc7, DG_MUL_WIDE(fl1, (i < L - 1) ? fe_sub(O(i + 1), nwi) : nwi));
+                wide_add(acc7, DG_MUL_WIDE(fl2, (i < L - 2) ? fe_sub(O(i + 2), nwi) : nwi));
+                wide_add(acc7, DG_MUL_WIDE(fl4, (i < L - 4) ? fe_sub(O(i + 4), nwi) : nwi));
+                return DG_REDUCE_WIDE(acc7);
+            }
             fe v = fe_mul(fc, fe_sub(O(i), nwi));
             if (i >= 1) v = fe_add(v, fe_mul(f_rs1, fe_sub(O(i - 1), nwi)));
             if (i >= 2) v = fe_add(v, fe_mul(f_rs2, fe_sub(O(i - 2), nwi)));
@@ -943,24 +956,27 @@ void launch_constraint_eval(Context &c, const AirParams &P) {
     air_upload_constants(c);
     const unsigned long long E = (unsigned long long)P.num_c8 << P.log_n;
     static int variant = -1;
-    if (variant < 0) { const char *e = getenv("DG_AIR_CFG"); variant = e ? atoi(e) : 6; }
+    if (variant < 0) { const char *e = getenv("DG_AIR_CFG"); variant = e ? atoi(e) : 7; }
 #define DG_AIR_LAUNCH(BLOCK, MINB) constraint_eval_kernel<BLOCK, MINB><<<(unsigned)((E + BLOCK - 1) / BLOCK), BLOCK, 0, c.stream>>>(P)
-#define DG_AIR_LAUNCH_SMEM(BLOCK, MINB, DEC)                                                                                         \
+#define DG_AIR_LAUNCH_SMEM(BLOCK, MINB, DEC, WIDE)                                                                                         \
     do {                                                                                                                             \
         const size_t smem = (size_t)(P.w - ((DEC) ? 0 : 15)) * (BLOCK + 1) * sizeof(fe);                                             \
-        auto k = constraint_eval_smem_kernel<BLOCK, MINB, DEC>;                                                                      \
+        auto k = constraint_eval_smem_kernel<BLOCK, MINB, DEC, WIDE>;                                                                      \
         set_func_smem(c, (const void *)k, smem);                                                                                     \
         k<<<(unsigned)(E / BLOCK), BLOCK, smem, c.stream>>>(P);                                                                      \
     } while (0)
     int v = variant;
     const unsigned long long n = 1ULL << P.log_n;
     // the shared-memory variants need whole blocks inside one coset and at most ~200 KB of rows per block
+    if (v < 5 || v > 7) v = 1;
     if (v >= 5 && (n < 128 || (size_t)P.w * 129 * sizeof(fe) > 200 * 1024)) v = 1;
     // B200, 2^20 steps x 26 registers: per-thread arrays (r01) (128 threads, 4 blocks/SM) 20.9 ms, (256, 2) 22.3, (256, 1) 28.1;
-    // shared-memory rows (r02): stack-like columns only (128, 4) 19.9 / (128, 3) 21.3; all columns (128, 4) 19.1 / (128, 3) 20.6
+    // shared-memory rows (r02): stack-like columns only (128, 4) 19.9 / (128, 3) 21.3; all columns (128, 4) 19.1 / (128, 3) 20.6;
+    // all columns + unreduced per-slot sums (128, 4) 18.6; the same at 5 blocks/SM (96 registers, stack-like columns only) 19.0
     switch (v) {
-        case 5: DG_AIR_LAUNCH_SMEM(128, 4, false); break;      // only the context / loop / stack columns staged
-        case 6: DG_AIR_LAUNCH_SMEM(128, 4, true); break;       // default
+        case 5: DG_AIR_LAUNCH_SMEM(128, 4, false, false); break;     // only the context / loop / stack columns staged
+        case 6: DG_AIR_LAUNCH_SMEM(128, 4, true, false); break;      // all columns staged
+        case 7: DG_AIR_LAUNCH_SMEM(128, 4, true, true); break;       // default: + unreduced accumulation of the seven products of a stack slot
         default: DG_AIR_LAUNCH(128, 4); break;                 // per-thread arrays: short traces (n < 128) and very wide ones
     }
     c.launches++;
