@@ -165,28 +165,4 @@ void fri_fold_local(Context &c, const fe *values_local, int log_d, int log_b, in
     DG_CUDA(cudaGetLastError());
 }
 
-// nodes[L/2 + j] = H(ev[4j], ev[4j+1], ev[4j+2], ev[4j+3]) with L = N/2 two-element leaves (prover.rs:84-86, 180-187)
-__global__ void __launch_bounds__(256) constraint_first_level_kernel(const fe *__restrict__ ev, int log_n, int log_blowup, uint4 *__restrict__ nodes) {
-    const unsigned long long n = 1ULL << log_n;
-    const unsigned long long quarter = (n << log_blowup) >> 2;
-    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= quarter) return;
-    const unsigned long long c4 = t >> log_n, k = t & (n - 1);
-    const unsigned long long j = (k << (log_blowup - 2)) + c4;
-    uint32_t m[16], cv[8];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-        const uint4 x = reinterpret_cast<const uint4 *>(ev)[(4 * c4 + u) * n + k];
-        m[4 * u] = x.x; m[4 * u + 1] = x.y; m[4 * u + 2] = x.z; m[4 * u + 3] = x.w;
-    }
-    b3::hash64(m, cv);
-    nodes[2 * (quarter + j)] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
-    nodes[2 * (quarter + j) + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
-}
-void constraint_tree_first_level(Context &c, const fe *evals, int log_n, int log_blowup, void *nodes) {
-    const unsigned long long quarter = (1ULL << (log_n + log_blowup)) >> 2;
-    constraint_first_level_kernel<<<(unsigned)((quarter + 255) / 256), 256, 0, c.stream>>>(evals, log_n, log_blowup, (uint4 *)nodes); c.launches++;
-    DG_CUDA(cudaGetLastError());
-}
-
 }  // namespace dg

@@ -61,7 +61,5 @@ void fri_alpha(Context &c, const void *root_dev, fe *alpha_dev, void *root_copy_
 void fri_hash_rows_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, void *items_local);
 void fri_fold_local(Context &c, const fe *values_local, int log_d, int log_b, int log_nc, unsigned c0, fe *next_local, const fe *alpha,
                     const TwiddleRef &inv_root_table, int log_n_total, fe tau_inv, fe inv4);
-// first level of the constraint tree straight from coset-major evaluations: nodes[L/2 + j] = H(ev[4j..4j+3]), L = N/2 leaves
-void constraint_tree_first_level(Context &c, const fe *evals, int log_n, int log_blowup, void *nodes);
 
 }  // namespace dg

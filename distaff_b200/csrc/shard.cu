@@ -36,21 +36,7 @@ ShardLocation ShardGeom::node(uint64_t h) const {
 }
 
 // ---- kernels ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) hash_pairs_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, unsigned long long count) {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    uint32_t m[16], cv[8];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        uint4 v = in[4 * i + q];
-        m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
-    }
-    b3::hash64(m, cv);
-    out[2 * i] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
-    out[2 * i + 1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
-}
-
-// levels of a heap-layout tree from L/2 nodes down to (and including) the level with `stop` nodes (hash.cu: fused levels)
+// levels of a heap-layout tree from L/2 nodes down to (and including) the level with `stop` nodes (hash.cu)
 void merkle_levels_down_to(Context &c, const void *leaves, void *nodes, unsigned long long L, unsigned long long stop);
 void merkle_build_partial(Context &c, const void *leaves, void *nodes, unsigned long long L, unsigned long long stop) {
     merkle_levels_down_to(c, leaves, nodes, L, stop);
@@ -68,22 +54,6 @@ __global__ void interleave_roots_kernel(const uint4 *__restrict__ gathered, uint
 void interleave_roots(Context &c, const void *gathered, void *upper, unsigned long long n, int log_g) {
     const unsigned long long total = n << log_g;
     interleave_roots_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>((const uint4 *)gathered, (uint4 *)upper, n, log_g); c.launches++;
-    DG_CUDA(cudaGetLastError());
-}
-
-// out[b][k][c] = in[b][c][k]
-__global__ void transpose_cosets_kernel(const fe *__restrict__ in, fe *__restrict__ out, int log_n, int log_c) {
-    const unsigned long long n = 1ULL << log_n;
-    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int C = 1 << log_c;
-    const fe *src = in + ((unsigned long long)blockIdx.y << (log_n + log_c));
-    fe *dst = out + ((unsigned long long)blockIdx.y << (log_n + log_c)) + (k << log_c);
-    for (int cc = 0; cc < C; cc++) dst[cc] = src[(unsigned long long)cc * n + k];
-}
-void transpose_cosets(Context &c, const fe *in, fe *out, int log_n, int log_c, int batch) {
-    const unsigned long long n = 1ULL << log_n;
-    transpose_cosets_kernel<<<dim3((unsigned)((n + 127) / 128), batch), 128, 0, c.stream>>>(in, out, log_n, log_c); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 

@@ -88,7 +88,6 @@ void merkle_build_partial(Context &c, const void *leaves, void *nodes, unsigned 
 void merkle_build(Context &c, const void *leaves, void *nodes, unsigned long long L);
 void merkle_finish(Context &c, void *nodes, unsigned long long m);
 void interleave_roots(Context &c, const void *gathered, void *upper, unsigned long long n, int log_g);
-void transpose_cosets(Context &c, const fe *in, fe *out, int log_n, int log_c, int batch);   // [batch][2^log_c][n] -> [batch][n][2^log_c]
 void constraint_items_local(Context &c, const fe *evals_local, int log_n, int log_nc, void *items);   // [k][c4_local] digests
 
 }  // namespace dg
