@@ -20,6 +20,11 @@ std::string verify_proof(Context &c, const uint8_t program_hash[32], const std::
                          const uint8_t *proof_bytes, size_t proof_len);
 }
 
+namespace dg {
+bool host_plan_verify_batch(const std::vector<uint64_t> &indexes, int depth, size_t n_values, const std::vector<uint32_t> &node_counts,
+                            std::vector<uint32_t> &ops, std::vector<uint32_t> &level_start, uint32_t &root_slot);
+}
+
 using namespace dg;
 
 static thread_local std::string t_last_error;
@@ -474,6 +479,24 @@ int dg_host_plan_batch(const uint64_t *indexes, uint32_t n_indexes, uint64_t n_l
         DG_REQUIRE(flat.size() <= cap, "buffer too small");
         memcpy(out, flat.data(), flat.size() * 8);
         *written = flat.size();
+    });
+}
+int dg_host_merkle_verify_plan(const uint64_t *indexes, uint32_t n_indexes, uint32_t depth, uint32_t n_values, const uint32_t *node_counts,
+                               uint32_t n_slots, uint32_t *ops, size_t ops_cap, uint32_t *n_ops, uint32_t *level_start, size_t levels_cap,
+                               uint32_t *n_levels, uint32_t *root_slot) {
+    return guarded([&] {
+        DG_REQUIRE(indexes && node_counts && ops && n_ops && level_start && n_levels && root_slot, "null argument");
+        std::vector<uint32_t> o, ls;
+        uint32_t root = 0;
+        if (!host_plan_verify_batch(std::vector<uint64_t>(indexes, indexes + n_indexes), (int)depth, n_values,
+                                    std::vector<uint32_t>(node_counts, node_counts + n_slots), o, ls, root))
+            throw Error(DG_ERR_REJECTED, "batch proof structure rejected (merkle.rs:154-263 returns false)");
+        DG_REQUIRE(o.size() <= ops_cap && ls.size() <= levels_cap, "buffer too small");
+        memcpy(ops, o.data(), o.size() * 4);
+        memcpy(level_start, ls.data(), ls.size() * 4);
+        *n_ops = (uint32_t)(o.size() / 3);
+        *n_levels = (uint32_t)ls.size() - 1;
+        *root_slot = root;
     });
 }
 int dg_host_periodic_tables(uint8_t *out16) {

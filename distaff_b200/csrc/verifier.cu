@@ -306,6 +306,20 @@ bool remainder_is_low_degree(const std::vector<fe> &xs_all, const std::vector<fe
 
 }  // namespace
 
+// host-only view of the batch-Merkle hashing plan (CPU tests): values occupy pool slots [0, n_values), the nodes of slot i start at
+// n_values + sum of the earlier slots' sizes, computed parents follow.  Returns false where verify_batch returns false before hashing.
+bool host_plan_verify_batch(const std::vector<uint64_t> &indexes, int depth, size_t n_values, const std::vector<uint32_t> &node_counts,
+                            std::vector<uint32_t> &ops, std::vector<uint32_t> &level_start, uint32_t &root_slot) {
+    std::vector<std::vector<Digest>> nodes(node_counts.size());
+    std::vector<uint32_t> bases;
+    uint32_t next = (uint32_t)n_values;
+    for (size_t i = 0; i < node_counts.size(); i++) { nodes[i].resize(node_counts[i]); bases.push_back(next); next += node_counts[i]; }
+    MerklePlan p = plan_verify_batch(indexes, depth, n_values, 0, nodes, bases, next);
+    if (!p.ok) return false;
+    ops = p.ops; level_start = p.level_start; root_slot = p.root_slot;
+    return true;
+}
+
 // returns "" when the proof is accepted, the reference's error string otherwise; throws Error for malformed input / CUDA failures
 std::string verify_proof(Context &c, const uint8_t program_hash[32], const std::vector<fe> &inputs, const std::vector<fe> &outputs,
                          const uint8_t *proof_bytes, size_t proof_len) {

@@ -169,6 +169,13 @@ int dg_host_blake3(const uint8_t *data, size_t len, uint8_t out32[32]);
 /* MerkleTree::prove_batch planning (merkle.rs:64-124): writes, per normalised slot, the count and then (is_leaf, index) pairs;
  * out layout: [n_slots][depth] then for each slot [count] (is_leaf, index)*count, all uint64 */
 int dg_host_plan_batch(const uint64_t *indexes, uint32_t n_indexes, uint64_t n_leaves, uint64_t *out, size_t cap, size_t *written);
+/* MerkleTree::verify_batch (merkle.rs:154-263) as the hashing plan dg_verify executes on the device: digests live in a pool -- the proof's
+ * values in slots [0, n_values), the nodes of slot i from n_values + node_counts[0..i) on, computed parents after them; ops = (left, right,
+ * out) slot triples, level_start[l] .. level_start[l+1] the ops of level l; the tree is accepted iff pool[root_slot] equals the root.
+ * Returns DG_ERR_REJECTED where verify_batch returns false for structural reasons. */
+int dg_host_merkle_verify_plan(const uint64_t *indexes, uint32_t n_indexes, uint32_t depth, uint32_t n_values, const uint32_t *node_counts,
+                               uint32_t n_slots, uint32_t *ops, size_t ops_cap, uint32_t *n_ops, uint32_t *level_start, size_t levels_cap,
+                               uint32_t *n_levels, uint32_t *root_slot);
 /* extend_constants tables (constraints/utils.rs:87-113): 128 rows x 23 columns = sponge ARK 8 | masks 3 | hasher ARK 12 */
 int dg_host_periodic_tables(uint8_t *out16 /* 128*23 elements */);
 

@@ -239,3 +239,78 @@ def test_generator_against_the_published_chacha20_vector(L):
     buf = (ctypes.c_uint8 * 16)()
     assert L.dg_host_prng_vector(bytes(32), 1, buf) == 0
     assert int.from_bytes(bytes(buf), "little") == (v * M) >> 128
+
+
+def test_merkle_verification_plan_equals_verify_batch(L):
+    """The hashing plan dg_verify runs on the device (verifier.cu: plan_verify_batch, exported as dg_host_merkle_verify_plan) executed on the
+    CPU with blake3 must accept exactly what MerkleTree::verify_batch (merkle.rs:154-263, restated in the oracle) accepts: honest batch
+    proofs for random index sets, and the same proofs with a corrupted value / node / index set / node-list shape."""
+    import ctypes
+    import random
+    import struct
+    import blake3 as b3
+    from oracle import pyoracle as po
+    rng = random.Random(11)
+
+    def parse(proof):
+        off = 0
+        (nv,) = struct.unpack_from("<Q", proof, off); off += 8
+        values = [proof[off + 32 * i: off + 32 * i + 32] for i in range(nv)]; off += 32 * nv
+        (ns,) = struct.unpack_from("<Q", proof, off); off += 8
+        nodes = []
+        for _ in range(ns):
+            (k,) = struct.unpack_from("<Q", proof, off); off += 8
+            nodes.append([proof[off + 32 * i: off + 32 * i + 32] for i in range(k)]); off += 32 * k
+        return values, nodes, proof[off]
+
+    def encode(values, nodes, depth):
+        out = struct.pack("<Q", len(values)) + b"".join(values) + struct.pack("<Q", len(nodes))
+        for slot in nodes:
+            out += struct.pack("<Q", len(slot)) + b"".join(slot)
+        return out + bytes([depth])
+
+    def run_plan(root, indexes, values, nodes, depth):
+        counts = (ctypes.c_uint32 * max(1, len(nodes)))(*[len(s) for s in nodes])
+        idx = (ctypes.c_uint64 * max(1, len(indexes)))(*indexes)
+        ops = (ctypes.c_uint32 * 30000)()
+        ls = (ctypes.c_uint32 * 64)()
+        n_ops, n_levels, root_slot = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
+        rc = L.dg_host_merkle_verify_plan(idx, len(indexes), depth, len(values), counts, len(nodes), ops, 30000, ctypes.byref(n_ops), ls, 64,
+                                          ctypes.byref(n_levels), ctypes.byref(root_slot))
+        if rc != 0:
+            return False
+        pool = list(values) + [d for s in nodes for d in s]
+        pool += [None] * n_ops.value
+        for lvl in range(n_levels.value):
+            for o in range(ls[lvl], ls[lvl + 1]):
+                l, r, out = ops[3 * o], ops[3 * o + 1], ops[3 * o + 2]
+                pool[out] = b3.blake3(pool[l] + pool[r]).digest()
+        return pool[root_slot.value] == root
+
+    accepted = rejected = 0
+    for log_l in (3, 5, 8, 11):
+        n = 1 << log_l
+        leaves = bytes(rng.getrandbits(8) for _ in range(32 * n))
+        root = po.merkle_nodes("blake3", leaves)[32:64]
+        for trial in range(12):
+            k = rng.randrange(1, min(n, 40) + 1)
+            indexes = rng.sample(range(n), k)
+            proof = po.merkle_prove_batch("blake3", leaves, indexes)
+            values, nodes, depth = parse(proof)
+            cases = [(indexes, values, nodes, depth)]
+            v2 = list(values); v2[rng.randrange(len(v2))] = bytes(32); cases.append((indexes, v2, nodes, depth))
+            slots = [i for i, s in enumerate(nodes) if s]
+            if slots:
+                n2 = [list(s) for s in nodes]; s = rng.choice(slots); n2[s][rng.randrange(len(n2[s]))] = bytes(range(32)); cases.append((indexes, values, n2, depth))
+                n3 = [list(s) for s in nodes]; n3[rng.choice(slots)].pop(); cases.append((indexes, values, n3, depth))
+            other = [i ^ 1 for i in indexes]
+            if sorted(other) != sorted(indexes) and len(set(other)) == len(other):
+                cases.append((other, values, nodes, depth))
+            cases.append((indexes[:-1], values, nodes, depth) if k > 1 else (indexes, values, nodes[:-1], depth))
+            for idx, vals, nds, dep in cases:
+                want = po.merkle_verify_batch("blake3", root, idx, encode(vals, nds, dep))
+                got = run_plan(root, idx, vals, nds, dep)
+                assert want in (0, 1) and got == (want == 1), (log_l, trial, idx[:5])
+                accepted += got
+                rejected += not got
+    assert accepted >= 48 and rejected >= 100
