@@ -17,9 +17,11 @@ __device__ __forceinline__ fe pw(const PowRef &t, unsigned long long e) {
     return fe_mul(t.lo[e & ((1ULL << t.lo_bits) - 1ULL)], t.hi[e >> t.lo_bits]);
 }
 
-__global__ void pow_fill_kernel(fe *out, fe base, unsigned long long count) {
+// lo[i] = base^i (i < lo_n) and hi[i] = step^i (i < hi_n) in one launch
+__global__ void pow_fill_kernel(fe *lo, fe base, unsigned long long lo_n, fe *hi, fe step, unsigned long long hi_n) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = fe_pow_u64(base, i);
+    if (i < lo_n) lo[i] = fe_pow_u64(base, i);
+    else if (i < lo_n + hi_n) hi[i - lo_n] = fe_pow_u64(step, i - lo_n);
 }
 
 PowTable::PowTable(Context &c, fe base, unsigned long long len) {
@@ -30,8 +32,7 @@ PowTable::PowTable(Context &c, fe base, unsigned long long len) {
     lo.alloc(lo_n * sizeof(fe));
     hi.alloc(hi_n * sizeof(fe));
     fe step = fe_pow_u64(base, lo_n);
-    pow_fill_kernel<<<(unsigned)((lo_n + 127) / 128), 128, 0, c.stream>>>(lo.as<fe>(), base, lo_n); c.launches++;
-    pow_fill_kernel<<<(unsigned)((hi_n + 127) / 128), 128, 0, c.stream>>>(hi.as<fe>(), step, hi_n); c.launches++;
+    pow_fill_kernel<<<(unsigned)((lo_n + hi_n + 127) / 128), 128, 0, c.stream>>>(lo.as<fe>(), base, lo_n, hi.as<fe>(), step, hi_n); c.launches++;
     DG_CUDA(cudaGetLastError());
 }
 
