@@ -317,13 +317,14 @@ __global__ void lincomb2_kernel(const fe *__restrict__ polys, unsigned long long
                                 fe *__restrict__ t1, fe *__restrict__ t2) {
     unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    fe a = fe_make(0, 0), b = fe_make(0, 0);
+    // w < 128 products per sum: accumulated unreduced (288 bits), one reduction each (fp128.cuh: fe_wide)
+    fe_wide a, b;
     for (int i = 0; i < w; i++) {
-        fe v = polys[(unsigned long long)i * n + k];
-        a = fe_add(a, fe_mul(v, cc1[i]));
-        b = fe_add(b, fe_mul(v, cc2[i]));
+        const fe v = polys[(unsigned long long)i * n + k];
+        if (i == 0) { wide_set(a, DG_MUL_WIDE(v, cc1[0])); wide_set(b, DG_MUL_WIDE(v, cc2[0])); }
+        else { wide_add(a, DG_MUL_WIDE(v, cc1[i])); wide_add(b, DG_MUL_WIDE(v, cc2[i])); }
     }
-    t1[k] = a; t2[k] = b;
+    t1[k] = DG_REDUCE_WIDE(a); t2[k] = DG_REDUCE_WIDE(b);
 }
 void lincomb2(Context &c, const fe *polys, unsigned long long n, int w, const fe *cc1, const fe *cc2, fe *t1, fe *t2) {
     lincomb2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(polys, n, w, cc1, cc2, t1, t2); c.launches++;
@@ -340,14 +341,19 @@ __global__ void boundary_coeffs_kernel(const fe *__restrict__ polys, unsigned lo
                                        fe KfA, fe KfB, unsigned long long adj, fe *__restrict__ ic, fe *__restrict__ fc) {
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    fe ia = fe_make(0, 0), ib = ia, fa = ia, fb = ia;
+    // nb < 128 products per sum: accumulated unreduced (288 bits), one reduction each
+    fe_wide wa, wb, wc, wd;
     for (int j = 0; j < nb; j++) {
         const fe v = polys[(unsigned long long)j * n + k];
-        ia = fe_add(ia, fe_mul(v, coef[j]));
-        ib = fe_add(ib, fe_mul(v, coef[nb + j]));
-        fa = fe_add(fa, fe_mul(v, coef[2 * nb + j]));
-        fb = fe_add(fb, fe_mul(v, coef[3 * nb + j]));
+        if (j == 0) {
+            wide_set(wa, DG_MUL_WIDE(v, coef[0])); wide_set(wb, DG_MUL_WIDE(v, coef[nb])); wide_set(wc, DG_MUL_WIDE(v, coef[2 * nb]));
+            wide_set(wd, DG_MUL_WIDE(v, coef[3 * nb]));
+        } else {
+            wide_add(wa, DG_MUL_WIDE(v, coef[j])); wide_add(wb, DG_MUL_WIDE(v, coef[nb + j])); wide_add(wc, DG_MUL_WIDE(v, coef[2 * nb + j]));
+            wide_add(wd, DG_MUL_WIDE(v, coef[3 * nb + j]));
+        }
     }
+    fe ia = DG_REDUCE_WIDE(wa), ib = DG_REDUCE_WIDE(wb), fa = DG_REDUCE_WIDE(wc), fb = DG_REDUCE_WIDE(wd);
     if (k == 0) { ia = fe_sub(ia, KiA); ib = fe_sub(ib, KiB); fa = fe_sub(fa, KfA); fb = fe_sub(fb, KfB); }
     const fe zero = fe_make(0, 0);
     ic[k] = ia; fc[k] = fa;
