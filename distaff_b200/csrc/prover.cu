@@ -123,8 +123,9 @@ struct FriLayerDev {
 class TraceUploader {
 public:
     static const int WORKERS = 4, SLOTS = 2;
-    TraceUploader(Context &c, fe *d_regs, const uint8_t *const *host_cols, int w, uint64_t n, int chunk)
-        : c_(c), w_(w), chunk_(chunk), nchunks_((w + chunk - 1) / chunk), col_bytes_(n * 16), done_(nchunks_, nullptr), recorded_(nchunks_) {
+    // chunk i = columns [bounds[i], bounds[i + 1])
+    TraceUploader(Context &c, fe *d_regs, const uint8_t *const *host_cols, int w, uint64_t n, const std::vector<int> &bounds)
+        : c_(c), w_(w), bounds_(bounds), nchunks_((int)bounds.size() - 1), col_bytes_(n * 16), done_(nchunks_, nullptr), recorded_(nchunks_) {
         for (auto &r : recorded_) r.store(0);
         for (auto &e : done_) DG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         // the destination comes from the stream-ordered pool / arena of the compute stream: order the copies after it
@@ -138,7 +139,7 @@ public:
         if (pinned) {
             DG_CUDA(cudaStreamWaitEvent(c.copy_stream, ready, 0));
             for (int i = 0; i < nchunks_; i++) {           // enqueue every upload first: the copy engine runs ahead of the compute stream
-                for (int j = i * chunk; j < std::min(w, (i + 1) * chunk); j++)
+                for (int j = bounds_[i]; j < bounds_[i + 1]; j++)
                     DG_CUDA(cudaMemcpyAsync(d_regs + (size_t)j * n, host_cols[j], col_bytes_, cudaMemcpyHostToDevice, c.copy_stream));
                 DG_CUDA(cudaEventRecord(done_[i], c.copy_stream));
                 recorded_[i].store(1);
@@ -158,7 +159,7 @@ public:
                     int use = 0;
                     // worker t owns the chunks i = t, t + WORKERS, ... ; chunks complete in order per worker, the consumer waits per chunk
                     for (int i = t; i < nchunks_ && !failed_.load(); i += WORKERS) {
-                        for (int j = i * chunk_; j < std::min(w_, (i + 1) * chunk_); j++, use++) {
+                        for (int j = bounds_[i]; j < bounds_[i + 1]; j++, use++) {
                             const int s = use % SLOTS;
                             uint8_t *slot = (uint8_t *)c_.staging.p + ((size_t)t * SLOTS + s) * col_bytes_;
                             if (slot_free[s]) cudaEventSynchronize(slot_free[s]);
@@ -192,7 +193,9 @@ public:
     }
 private:
     Context &c_;
-    int w_, chunk_, nchunks_;
+    int w_;
+    std::vector<int> bounds_;
+    int nchunks_;
     size_t col_bytes_;
     std::vector<cudaEvent_t> done_;
     std::vector<std::atomic<int>> recorded_;
@@ -260,10 +263,13 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
             ntt_batch(c, d_regs, polys.as<fe>(), log_n, w, n, n, true);
             lde_batch(c, polys.as<fe>(), ext.as<fe>(), log_n, log_b, 1, w, n, N_loc, c0, (unsigned)nc);
         } else {
-            const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>(w, ((uint64_t)1 << 26) / (n * 16)));   // ~64 MB per upload
-            TraceUploader up(c, d_regs, host_cols, w, n, chunk);
+            // chunks of ~64 MB, but a short ramp first (1, 2 columns): the first transform starts after one column's worth of copying
+            const int chunk = (int)std::max<uint64_t>(1, std::min<uint64_t>(w, ((uint64_t)1 << 26) / (n * 16)));
+            std::vector<int> bounds = {0};
+            for (int step = 1; bounds.back() < w; step = std::min(chunk, step * 2)) bounds.push_back(std::min(w, bounds.back() + step));
+            TraceUploader up(c, d_regs, host_cols, w, n, bounds);
             for (int i = 0; i < up.chunks(); i++) {
-                const int j0 = i * chunk, cols = std::min(w, j0 + chunk) - j0;
+                const int j0 = bounds[i], cols = bounds[i + 1] - j0;
                 up.wait_chunk(i);
                 ntt_batch(c, d_regs + (size_t)j0 * n, polys.as<fe>() + (size_t)j0 * n, log_n, cols, n, n, true);
                 lde_batch(c, polys.as<fe>() + (size_t)j0 * n, ext.as<fe>() + (size_t)j0 * N_loc, log_n, log_b, 1, cols, n, N_loc, c0, (unsigned)nc);
@@ -274,7 +280,9 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
         DevBuf own((size_t)cpr * n * 16), slots((size_t)cpr * G * n * 16);
         if (mine > 0) {
             if (host_cols) {
-                TraceUploader up(c, d_regs + (size_t)j0 * n, host_cols + j0, mine, n, 1);      // one column per chunk: all staging workers busy
+                std::vector<int> bounds(mine + 1);
+                for (int i = 0; i <= mine; i++) bounds[i] = i;
+                TraceUploader up(c, d_regs + (size_t)j0 * n, host_cols + j0, mine, n, bounds);      // one column per chunk: all staging workers busy
                 for (int i = 0; i < up.chunks(); i++) up.wait_chunk(i);
                 ntt_batch(c, d_regs + (size_t)j0 * n, own.as<fe>(), log_n, mine, n, n, true);
             } else {
