@@ -283,8 +283,10 @@ static Proof *prove_core(Context &c, fe *d_regs, const uint8_t *const *host_cols
                 std::vector<int> bounds(mine + 1);
                 for (int i = 0; i <= mine; i++) bounds[i] = i;
                 TraceUploader up(c, d_regs + (size_t)j0 * n, host_cols + j0, mine, n, bounds);      // one column per chunk: all staging workers busy
-                for (int i = 0; i < up.chunks(); i++) up.wait_chunk(i);
-                ntt_batch(c, d_regs + (size_t)j0 * n, own.as<fe>(), log_n, mine, n, n, true);
+                for (int i = 0; i < up.chunks(); i++) {              // interpolate every column as soon as it has landed
+                    up.wait_chunk(i);
+                    ntt_batch(c, d_regs + (size_t)(j0 + i) * n, own.as<fe>() + (size_t)i * n, log_n, 1, n, n, true);
+                }
             } else {
                 ntt_batch(c, d_regs + (size_t)j0 * n, own.as<fe>(), log_n, mine, n, n, true);
             }
