@@ -2,6 +2,7 @@
 #include "host_fs.h"
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include "air_constants.h"
 #include "blake3.cuh"
@@ -56,14 +57,18 @@ uint64_t Rng::below(uint64_t range) {
     }
 }
 static RngHooks g_hooks = {nullptr, nullptr, nullptr};
+static std::mutex g_hooks_mu;              // single-process multi-GPU: the ranks are host threads; callbacks run one at a time
 void set_rng_hooks(const RngHooks *hooks) { if (hooks) g_hooks = *hooks; else g_hooks = RngHooks{nullptr, nullptr, nullptr}; }
 bool rng_hooks_active() { return g_hooks.draw_field != nullptr || g_hooks.draw_positions != nullptr; }
 
 std::vector<fe> prng_vector(const uint8_t seed[32], size_t count) {
     std::vector<fe> v(count);
     if (g_hooks.draw_field) {
-        if (g_hooks.draw_field(g_hooks.user, seed, count, reinterpret_cast<uint8_t *>(v.data())) != 0)
-            throw std::runtime_error("draw_field callback failed");
+        {
+            std::lock_guard<std::mutex> lk(g_hooks_mu);
+            if (g_hooks.draw_field(g_hooks.user, seed, count, reinterpret_cast<uint8_t *>(v.data())) != 0)
+                throw std::runtime_error("draw_field callback failed");
+        }
         for (auto &x : v)                                     // field::prng_vector yields canonical elements (Uniform over 0..M)
             if (x.hi == DG_M_HI && x.lo >= DG_M_LO) throw std::runtime_error("draw_field callback returned a non-canonical field element");
         return v;
@@ -170,8 +175,11 @@ CompositionCoefficients draw_composition_coefficients(const uint8_t constraint_r
 std::vector<uint64_t> query_positions(const uint8_t seed[32], uint64_t domain_size, uint64_t extension_factor, uint32_t num_queries) {
     if (g_hooks.draw_positions) {
         std::vector<uint64_t> got(num_queries);
-        if (g_hooks.draw_positions(g_hooks.user, seed, domain_size, (uint32_t)extension_factor, num_queries, got.data()) != 0)
-            throw std::runtime_error("needed more query positions than could be generated");
+        {
+            std::lock_guard<std::mutex> lk(g_hooks_mu);
+            if (g_hooks.draw_positions(g_hooks.user, seed, domain_size, (uint32_t)extension_factor, num_queries, got.data()) != 0)
+                throw std::runtime_error("needed more query positions than could be generated");
+        }
         for (size_t i = 0; i < got.size(); i++) {             // the invariants compute_query_positions guarantees (stark/utils/mod.rs:31-41)
             if (got[i] >= domain_size || got[i] % extension_factor == 0 || std::find(got.begin(), got.begin() + i, got[i]) != got.begin() + i)
                 throw std::runtime_error("draw_positions callback returned an invalid position set");

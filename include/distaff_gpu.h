@@ -78,7 +78,8 @@ int dg_prove_device(const void *d_registers, uint32_t width, uint64_t length, ui
  * both built on rand 0.7.3, which is not part of the reference tree.  By default the library uses its own restatement of that
  * generator (ChaCha20, rand's widening-multiply rejection sampling); a Rust host can instead register callbacks that call the real
  * functions, so that no third-party semantics are reproduced on this side of the boundary.  Callbacks return 0 on success; they are
- * called on the thread that calls dg_prove, 20-30 times per proof (once per commitment).  draw_field writes `count` canonical field
+ * called 20-30 times per proof (once per commitment), one at a time: on the thread that calls dg_prove, and after dg_init_devices(n) also
+ * from the library's per-device host threads (every rank derives the same challenges; the calls are serialised by a mutex).  draw_field writes `count` canonical field
  * elements (16 LE bytes each); draw_positions writes exactly num_queries distinct positions < domain_size, none a multiple of
  * extension_factor (anything else is rejected with DG_ERR_INVALID; a non-zero return maps to DG_ERR_EXHAUSTED like the reference's panic).
  * Passing NULL restores the built-in generator.  Process-wide; not to be changed while a proof is running. */
