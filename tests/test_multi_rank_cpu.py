@@ -117,3 +117,15 @@ def test_reference_arm_under_torchrun_prints_one_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "ms" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["steps"] == 1 and "2^12 steps" in d["config"]["workload"] and len(d["proof_sha256"]) == 64
+
+
+@pytest.mark.parametrize("workload", ["fibonacci", "merkle"])
+def test_reference_arm_other_workloads(workload):
+    """BASELINE configs 2 and 3 through the CPU arm (small sizes here): one JSON line, same-config naming, a proof digest"""
+    env = dict(os.environ, BENCH_REF_THREADS="2", BENCH_REF_BUDGET_S="30")
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--workload", workload, "--log-n", "12", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["impl"] == "reference" and "2^12 steps" in d["config"]["workload"] and d["metric"].startswith("prove ms for 2^12-step trace")
+    assert d["cpu_baseline"]["cores"] == 2 and d["steps"] == 1 and len(d["proof_sha256"]) == 64 and len(d["stage_ms"]) == 9
